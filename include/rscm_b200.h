@@ -1,0 +1,267 @@
+/*
+ * rscm_b200.h — C ABI of the B200-native RSCM ensemble engine.
+ *
+ * This is the drop-in boundary for ONE path of lewisjared/rscm (v0.5.0): many
+ * independent `Model::run` calls (parameter sets x scenarios) of a component
+ * graph, i.e. `ModelRunner::run_batch` and what it calls.  A Rust `-sys` crate,
+ * a ctypes/cffi module or C++ code binds exactly these symbols; there are no
+ * torch / C++ types in any signature.  `INTEGRATION.md` shows the reference-side
+ * bindings.  Citations are relative to the reference checkout.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative RSCM_B200_E* code on error;
+ *    `rscm_b200_last_error(h)` (or `rscm_b200_last_global_error()` when no handle
+ *    exists yet) returns the message.  Nothing throws or aborts across the ABI.
+ *  - per-member numerical failure is DATA, not an error: outputs are NaN, the
+ *    status byte is set, the log-posterior is -inf (reference:
+ *    crates/rscm-core/src/model/runtime.rs:493-495,
+ *    crates/rscm-calibrate/src/sampler/ensemble.rs:152-176).
+ *  - the caller owns every buffer it passes; the handle owns device scratch and
+ *    the compiled graph.  A handle is not re-entrant (one call in flight) but
+ *    may be moved between host threads.
+ *  - there is NO CPU fallback: creation fails with RSCM_B200_ENODEVICE when no
+ *    CUDA device is usable, and RSCM_B200_EUNSUPPORTED for a graph the engine
+ *    has no device code for.
+ */
+#ifndef RSCM_B200_H
+#define RSCM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSCM_B200_ABI_VERSION 1
+
+/* error codes */
+#define RSCM_B200_OK 0
+#define RSCM_B200_EINVAL (-1)       /* bad argument / graph description */
+#define RSCM_B200_EUNSUPPORTED (-2) /* graph has no device program */
+#define RSCM_B200_ENODEVICE (-3)    /* no usable CUDA device */
+#define RSCM_B200_ECUDA (-4)        /* CUDA runtime error */
+#define RSCM_B200_ENOMEM (-5)
+
+/* Component kinds.  Replaces `Arc<dyn Component>` objects added through
+ * ModelBuilder::with_component (crates/rscm-core/src/model/builder.rs:45-60);
+ * parameter block order per kind is documented at rscm_b200_component_desc. */
+typedef enum {
+    RSCM_B200_TWO_LAYER = 1,    /* crates/rscm-two-layer/src/component.rs:38-90 */
+    RSCM_B200_CARBON_CYCLE = 2, /* crates/rscm-components/src/components/carbon_cycle.rs:24-40 */
+    RSCM_B200_CO2_ERF = 3,      /* crates/rscm-components/src/components/co2_erf.rs:18-25 */
+    RSCM_B200_GHG_FORCING = 5   /* crates/rscm-magicc/src/parameters/ghg_forcing.rs */
+} rscm_b200_component_kind;
+
+/* GridType — crates/rscm-core/src/component.rs:56-64 */
+typedef enum { RSCM_B200_SCALAR = 0, RSCM_B200_FOUR_BOX = 1, RSCM_B200_HEMISPHERIC = 2 } rscm_b200_grid;
+/* AggregateOp — crates/rscm-core/src/schema.rs:60-80 */
+typedef enum { RSCM_B200_AGG_SUM = 0, RSCM_B200_AGG_MEAN = 1, RSCM_B200_AGG_WEIGHTED = 2 } rscm_b200_agg_op;
+/* VariableSource — crates/rscm-core/src/state/mod.rs:157-170 */
+typedef enum { RSCM_B200_SRC_EXOGENOUS = 0, RSCM_B200_SRC_OWN_STATE = 1, RSCM_B200_SRC_UPSTREAM = 2 } rscm_b200_source;
+
+/* One component, in insertion order (the order decides variable-source
+ * classification, builder.rs:465-485).  Parameter block order:
+ *   TWO_LAYER    : lambda0, a, efficacy, eta, heat_capacity_surface, heat_capacity_deep
+ *   CARBON_CYCLE : tau, conc_pi, alpha_temperature, step_size (SolverOptions, default 0.1)
+ *   CO2_ERF      : erf_2xco2, conc_pi
+ *   GHG_FORCING  : method(0 Ipcctar,1 Olbl), co2_pi, ch4_pi, n2o_pi, delq2xco2, ch4_radeff,
+ *                  n2o_radeff, olbl_co2_a1,b1,c1,d1, olbl_ch4_a3,b3,d3, olbl_n2o_a2,b2,c2,d2,
+ *                  adjust_co2, adjust_ch4, adjust_n2o
+ */
+typedef struct {
+    int32_t kind;     /* rscm_b200_component_kind */
+    int32_t n_params;
+    const double *params;
+} rscm_b200_component_desc;
+
+/* VariableSchema::add_variable — crates/rscm-core/src/schema.rs */
+typedef struct {
+    const char *name;
+    int32_t grid; /* rscm_b200_grid */
+} rscm_b200_schema_variable;
+
+/* VariableSchema::add_aggregate — schema.rs; contributors in declaration order;
+ * list chained aggregates in dependency order. */
+typedef struct {
+    const char *name;
+    int32_t op;   /* rscm_b200_agg_op */
+    int32_t grid; /* rscm_b200_grid */
+    int32_t n_contributors;
+    const char *const *contributors;
+    const double *weights; /* n_contributors, AGG_WEIGHTED only, else NULL */
+} rscm_b200_aggregate_desc;
+
+typedef struct {
+    const char *name;
+    double value;
+} rscm_b200_initial_value;
+
+/* unit conversion factor applied on read for one (variable, consuming component)
+ * pair — model/runtime.rs:385-389; computed by the caller's unit registry. */
+typedef struct {
+    int32_t component; /* index into components[] */
+    const char *variable;
+    double factor;
+} rscm_b200_unit_factor;
+
+/* The description ModelBuilder holds when build() is called
+ * (crates/rscm-core/src/model/builder.rs:29-41). */
+typedef struct {
+    int32_t abi_version; /* RSCM_B200_ABI_VERSION */
+    int32_t n_components;
+    const rscm_b200_component_desc *components;
+    int32_t has_schema;
+    int32_t n_schema_variables;
+    const rscm_b200_schema_variable *schema_variables;
+    int32_t n_aggregates;
+    const rscm_b200_aggregate_desc *aggregates;
+    int32_t n_initial_values;
+    const rscm_b200_initial_value *initial_values;
+    int32_t n_unit_factors;
+    const rscm_b200_unit_factor *unit_factors;
+    const double *four_box_weights;    /* 4 or NULL (default 0.25 each) */
+    const double *hemispheric_weights; /* 2 or NULL (default 0.5 each) */
+    int32_t n_times;                   /* T = time_axis.len() */
+    const double *time_bounds;         /* T+1 (TimeAxis bounds, timeseries.rs:24-26) */
+    int32_t compute_dtype;             /* 0 = fp64 (parity path), 1 = fp32 (1e-4 path) */
+    int32_t device;                    /* CUDA device ordinal, -1 = current */
+} rscm_b200_graph_desc;
+
+typedef struct rscm_b200_ensemble rscm_b200_ensemble;
+
+/* ---- lifetime ----------------------------------------------------------- */
+/* Replaces ModelBuilder::build (builder.rs:418-860) once per ensemble instead
+ * of once per member (model_runner.rs:233-235). */
+int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemble **out);
+void rscm_b200_ensemble_destroy(rscm_b200_ensemble *h);
+const char *rscm_b200_last_error(const rscm_b200_ensemble *h);
+const char *rscm_b200_last_global_error(void);
+int rscm_b200_abi_version(void);
+int rscm_b200_device_count(void);
+
+/* ---- introspection (Model::debug_info equivalents, model/debug.rs:315-319) -- */
+int rscm_b200_n_variables(const rscm_b200_ensemble *h);
+const char *rscm_b200_variable_name(const rscm_b200_ensemble *h, int v);
+int rscm_b200_variable_grid(const rscm_b200_ensemble *h, int v);
+int rscm_b200_variable_is_endogenous(const rscm_b200_ensemble *h, int v);
+int rscm_b200_variable_index(const rscm_b200_ensemble *h, const char *name);
+/* exogenous variables, in the order scenario arrays must list them */
+int rscm_b200_n_exogenous(const rscm_b200_ensemble *h);
+int rscm_b200_exogenous_variable(const rscm_b200_ensemble *h, int i);
+/* nodes = components then aggregators; order[] receives node ids in BFS order
+ * (model/runtime.rs:504-510); returns the count */
+int rscm_b200_n_nodes(const rscm_b200_ensemble *h);
+int rscm_b200_execution_order(const rscm_b200_ensemble *h, int *order, int capacity);
+int rscm_b200_variable_source(const rscm_b200_ensemble *h, int component, const char *variable);
+/* canonical text of the fused device program chosen for this graph */
+const char *rscm_b200_program_signature(const rscm_b200_ensemble *h);
+/* index of the time point whose "{:.6}" key equals that of `time`
+ * (crates/rscm-calibrate/src/likelihood.rs:40-42); -1 if none */
+int rscm_b200_time_index(const rscm_b200_ensemble *h, double time);
+
+/* ---- per-member parameter binding ---------------------------------------- */
+/* Replaces the `factory(params) -> Model` closure of DefaultModelRunner
+ * (model_runner.rs:116-129, 233-235): column j of the parameter matrix feeds
+ * the named slot(s).  Slot names: "<ComponentType>.<field>" (first component
+ * of that type), "<ComponentType>#<i>.<field>" (i-th component overall) or
+ * "initial:<variable name>".  A column may appear several times (e.g. conc_pi of
+ * CarbonCycle and CO2ERF).  Unbound slots keep the graph description's value.
+ */
+int rscm_b200_bind_parameters(rscm_b200_ensemble *h, int n_bindings, const char *const *slots,
+                              const int32_t *columns, int n_columns);
+
+/* ---- output selection ------------------------------------------------------ */
+/* DefaultModelRunner::output_variables (model_runner.rs:124) plus a time
+ * sub-range; default after create = every variable, every time point. */
+int rscm_b200_select_outputs(rscm_b200_ensemble *h, int n_vars, const int32_t *vars,
+                             int32_t t_start, int32_t t_stop, int32_t t_step);
+/* rows of the output matrix = sum over selected vars of n_regions * n_selected_times */
+int64_t rscm_b200_output_rows(const rscm_b200_ensemble *h);
+
+/* ---- run: ModelRunner::run_batch (model_runner.rs:261-266) ---------------- */
+/* params   : [n_columns][M] (layout 0, SoA) or [M][n_columns] (layout 1, the
+ *            reference's &[Vec<f64>])
+ * scenarios: [S][n_exogenous][T][R_v]   (R_v regions of that variable)
+ * out      : [rows][S*M], run index = s*M + m; row order = selected variable,
+ *            then time, then region: Timeseries storage [T][R]
+ *            (timeseries.rs:261-275), NaN where the reference leaves NaN
+ * status   : [S*M] bit0 = a component failed / get_last_step assertion would fire,
+ *            bit1 = a non-finite value was produced; may be NULL
+ * All pointers are DEVICE pointers; work is enqueued on `stream`
+ * (a cudaStream_t, NULL = default stream) and is asynchronous.
+ */
+int rscm_b200_run_device(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
+                         const double *scenarios, int64_t S, double *out, uint8_t *status,
+                         void *stream);
+/* Same with HOST pointers: chunks members, overlaps H2D / kernel / D2H on two
+ * streams, returns when `out` is complete.  Pinned host memory gives full PCIe rate. */
+int rscm_b200_run_host(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
+                       const double *scenarios, int64_t S, double *out, uint8_t *status);
+
+/* ---- calibration: log-posterior per member -------------------------------- */
+/* Observation = crates/rscm-calibrate/src/target.rs:25; time already resolved
+ * to an index with rscm_b200_time_index. */
+typedef struct {
+    int32_t variable;   /* model variable index (scalar variables only, model_runner.rs:175-190) */
+    int32_t time_index;
+    double value;
+    double sigma;
+} rscm_b200_obs;
+
+typedef enum {
+    RSCM_B200_PRIOR_NONE = 0,
+    RSCM_B200_PRIOR_UNIFORM = 1,        /* a=low, b=high     distribution.rs:157-163 */
+    RSCM_B200_PRIOR_NORMAL = 2,         /* a=mean, b=std     distribution.rs:256-259 */
+    RSCM_B200_PRIOR_LOGNORMAL = 3,      /* a=mu, b=sigma     distribution.rs:353-360 */
+    RSCM_B200_PRIOR_BOUND_NORMAL = 4,   /* Bound{Normal}     distribution.rs:490-497 */
+    RSCM_B200_PRIOR_BOUND_LOGNORMAL = 5,
+    RSCM_B200_PRIOR_BOUND_UNIFORM = 6
+} rscm_b200_prior_kind;
+
+typedef struct {
+    int32_t kind;
+    int32_t reserved;
+    double a, b;
+    double low, high;
+} rscm_b200_prior;
+
+/* Target + GaussianLikelihood{normalize} (likelihood.rs:99-253); observations
+ * grouped by variable in Target order. */
+int rscm_b200_set_target(rscm_b200_ensemble *h, const rscm_b200_obs *obs, int64_t n_obs, int normalize);
+/* ParameterSet (parameter_set.rs:255-270): one prior per parameter column, or n=0 for none */
+int rscm_b200_set_priors(rscm_b200_ensemble *h, const rscm_b200_prior *priors, int n_columns);
+
+/* ensemble-level summary of a log-posterior evaluation (warp-shuffle + block reduction) */
+typedef struct {
+    double max_logpost;
+    int64_t argmax;    /* run index of the maximum, -1 if none finite */
+    double sum_finite; /* sum of finite log-posteriors */
+    int64_t n_finite;
+    int64_t n_runs;
+} rscm_b200_logpost_summary;
+
+/* EnsembleSampler::log_posterior_batch (sampler/ensemble.rs:143-178) fused into
+ * the member loop: no timeseries is written, 8 B per run.  Device pointers;
+ * `summary` (device, may be NULL) receives the block-reduced summary. */
+int rscm_b200_logpost_device(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
+                             const double *scenarios, int64_t S, double *logpost,
+                             rscm_b200_logpost_summary *summary, void *stream);
+int rscm_b200_logpost_host(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
+                           const double *scenarios, int64_t S, double *logpost,
+                           rscm_b200_logpost_summary *summary);
+
+/* ---- measurement helpers --------------------------------------------------- */
+/* number of engine kernels launched through this handle since creation */
+int64_t rscm_b200_launch_count(const rscm_b200_ensemble *h);
+/* average device time (ms, CUDA events on the launch stream) of the main fused
+ * kernel over the launches since the last reset; 0 if none */
+double rscm_b200_kernel_ms(rscm_b200_ensemble *h, int reset);
+/* DFMA-saturating micro-benchmark: measured FP64 (or FP32 when dtype=1) FMA
+ * throughput of `device` in TFLOP/s (2 flop per FMA) */
+int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSCM_B200_H */

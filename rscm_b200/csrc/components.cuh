@@ -1,0 +1,266 @@
+// components.cuh — device-side physics of the component kinds on the ensemble
+// hot path.  One call = one component solve for one member and one time step;
+// all operands live in registers.  Included by the fused member-loop kernel
+// (kernel.cuh) through the program structs the graph compiler emits.
+//
+// Calling convention (what graph.cpp's emitter generates):
+//   <kind>_prepare<R>(P, D)            once per member: derived constants
+//   <kind>_solve<R>(P, D, in, out, ..) once per step; `in` / `out` follow the
+//       reference's inputs() / outputs() order (definitions order = inputs,
+//       outputs, states: crates/rscm-macros/src/lib.rs:630-636), regions
+//       expanded; returns false when the reference's solve would fail
+//       (outputs then stay NaN, model/runtime.rs:493-495).
+//
+// Arithmetic follows the reference expression by expression except where noted
+// ("hoisted" / "reciprocal"): those re-associations change results by O(1 ulp)
+// per operation, far inside the 1e-9 relative parity bar (fp64).
+#pragma once
+
+namespace rscm_dev {
+
+template <class R> __device__ __forceinline__ R r_exp(R x);
+template <> __device__ __forceinline__ double r_exp<double>(double x) { return exp(x); }
+template <> __device__ __forceinline__ float r_exp<float>(float x) { return expf(x); }
+template <class R> __device__ __forceinline__ R r_log(R x);
+template <> __device__ __forceinline__ double r_log<double>(double x) { return log(x); }
+template <> __device__ __forceinline__ float r_log<float>(float x) { return logf(x); }
+template <class R> __device__ __forceinline__ R r_sqrt(R x);
+template <> __device__ __forceinline__ double r_sqrt<double>(double x) { return sqrt(x); }
+template <> __device__ __forceinline__ float r_sqrt<float>(float x) { return sqrtf(x); }
+template <class R> __device__ __forceinline__ R r_pow(R x, R y);
+template <> __device__ __forceinline__ double r_pow<double>(double x, double y) { return pow(x, y); }
+template <> __device__ __forceinline__ float r_pow<float>(float x, float y) { return powf(x, y); }
+template <class R> __device__ __forceinline__ R r_nan();
+template <> __device__ __forceinline__ double r_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+template <> __device__ __forceinline__ float r_nan<float>() { return __int_as_float(0x7fc00000); }
+
+// ---------------------------------------------------------------------------
+// TwoLayer — crates/rscm-two-layer/src/component.rs
+//   P: lambda0, a, efficacy, eta, heat_capacity_surface, heat_capacity_deep
+//   D: efficacy*eta, 1/Cs, eta/Cd
+//   in : erf (get()), Ts (at_start), Td (at_start)      out: Ts, Td
+// RK4 (ode_solvers 0.6.1 as called from rscm-core/src/ivp/mod.rs:245-253):
+// nsub fixed steps of h = 0.1 (component.rs:240); the third state (cumulative
+// heat, y0[2]=0, component.rs:236,186-187) is integrated and discarded by the
+// reference, so it is not computed here.
+// ---------------------------------------------------------------------------
+constexpr int TWO_LAYER_NP = 6;
+constexpr int TWO_LAYER_ND = 3;
+
+template <class R>
+__device__ __forceinline__ void two_layer_prepare(const R *P, R *D)
+{
+    D[0] = P[2] * P[3];    // efficacy * eta (same association as component.rs:176)
+    D[1] = R(1) / P[4];    // reciprocal of heat_capacity_surface
+    D[2] = P[3] / P[5];    // eta / heat_capacity_deep
+}
+
+template <class R>
+__device__ __forceinline__ void two_layer_rhs(R lam0, R a, R eff_eta, R inv_cs, R eta_cd, R erf,
+                                              R ts, R td, R &dts, R &dtd)
+{
+    // calculate_dy_dt — component.rs:160-188
+    const R diff = ts - td;
+    const R lambda_eff = lam0 - a * ts;
+    dts = (erf - lambda_eff * ts - eff_eta * diff) * inv_cs;
+    dtd = diff * eta_cd;
+}
+
+template <class R>
+__device__ __forceinline__ bool two_layer_solve(const R *P, const R *D, const R *in, R *out, int nsub)
+{
+    if (nsub < 0) return false; // get_last_step assertion (ivp/mod.rs:94-97) would fire
+    const R lam0 = P[0], a = P[1];
+    const R eff_eta = D[0], inv_cs = D[1], eta_cd = D[2];
+    const R erf = in[0];
+    R ts = in[1], td = in[2];
+    const R h = R(0.1), hh = R(0.1) / R(2), h6 = R(0.1) / R(6);
+#pragma unroll 2
+    for (int s = 0; s < nsub; ++s) {
+        R a0, b0, a1, b1, a2, b2, a3, b3;
+        two_layer_rhs(lam0, a, eff_eta, inv_cs, eta_cd, erf, ts, td, a0, b0);
+        two_layer_rhs(lam0, a, eff_eta, inv_cs, eta_cd, erf, ts + a0 * hh, td + b0 * hh, a1, b1);
+        two_layer_rhs(lam0, a, eff_eta, inv_cs, eta_cd, erf, ts + a1 * hh, td + b1 * hh, a2, b2);
+        two_layer_rhs(lam0, a, eff_eta, inv_cs, eta_cd, erf, ts + a2 * h, td + b2 * h, a3, b3);
+        ts = ts + (a0 + a1 * R(2) + a2 * R(2) + a3) * h6;
+        td = td + (b0 + b1 * R(2) + b2 * R(2) + b3) * h6;
+    }
+    out[0] = ts;
+    out[1] = td;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// CarbonCycle — crates/rscm-components/src/components/carbon_cycle.rs
+//   P: tau, conc_pi, alpha_temperature, step_size
+//   D: 1/tau
+//   in : emissions (get), temperature (get), concentration, cumulative_emissions,
+//        cumulative_uptake (at_start)      out: same three states
+// Hoisted per annual step (inputs are frozen over the step, :144-145):
+//   1/lifetime = exp(-alpha*T) / tau ;  E/GTC_PER_PPM
+// dy[2] = E is constant over the step, so its RK4 increment is one value.
+// ---------------------------------------------------------------------------
+constexpr int CARBON_CYCLE_NP = 4;
+constexpr int CARBON_CYCLE_ND = 1;
+
+template <class R>
+__device__ __forceinline__ void carbon_cycle_prepare(const R *P, R *D)
+{
+    D[0] = R(1) / P[0];
+}
+
+template <class R>
+__device__ __forceinline__ bool carbon_cycle_solve(const R *P, const R *D, const R *in, R *out, int nsub)
+{
+    if (nsub < 0) return false;
+    const R gtc = R(2.13); // GTC_PER_PPM, crates/rscm-components/src/constants.rs:37
+    const R conc_pi = P[1], alpha = P[2], h = P[3];
+    const R emissions = in[0], temperature = in[1];
+    R conc = in[2], cum_e = in[3], cum_u = in[4];
+    const R inv_life = r_exp<R>(-(alpha * temperature)) * D[0];
+    const R e_ppm = emissions / gtc;
+    const R hh = h / R(2), h6 = h / R(6);
+    const R e_inc = (emissions + emissions * R(2) + emissions * R(2) + emissions) * h6;
+    // The concentration is integrated as the anomaly x = C - C_pi (exact subtraction for
+    // C within a factor 2 of C_pi), so uptake u = x/lifetime is one multiply and is
+    // exactly 0 at C = C_pi as in the reference.  dC = e_ppm - u; dU = u*GTC; the
+    // weighted stage sums are formed once on u: sum(dC) = 6 e_ppm - su, sum(dU) = su*GTC.
+    const R e6 = e_ppm * R(6);
+    const R gtc_h6 = gtc * h6;
+    R x = conc - conc_pi;
+#pragma unroll 2
+    for (int s = 0; s < nsub; ++s) {
+        // calculate_dy_dt — carbon_cycle.rs:134-158
+        const R u0 = x * inv_life;
+        const R u1 = (x + (e_ppm - u0) * hh) * inv_life;
+        const R u2 = (x + (e_ppm - u1) * hh) * inv_life;
+        const R u3 = (x + (e_ppm - u2) * h) * inv_life;
+        const R su = u0 + u1 * R(2) + u2 * R(2) + u3;
+        x = x + (e6 - su) * h6;
+        cum_u = cum_u + su * gtc_h6;
+        cum_e = cum_e + e_inc;
+    }
+    conc = x + conc_pi;
+    out[0] = conc;
+    out[1] = cum_e;
+    out[2] = cum_u;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// CO2ERF — crates/rscm-components/src/components/co2_erf.rs:57-60
+//   P: erf_2xco2, conc_pi      D: erf_2xco2 / ln 2
+// ---------------------------------------------------------------------------
+constexpr int CO2_ERF_NP = 2;
+constexpr int CO2_ERF_ND = 1;
+
+template <class R>
+__device__ __forceinline__ void co2_erf_prepare(const R *P, R *D)
+{
+    D[0] = P[0] / R(0.6931471805599453094172321);
+}
+
+template <class R>
+__device__ __forceinline__ bool co2_erf_solve(const R *P, const R *D, const R *in, R *out, int)
+{
+    out[0] = D[0] * r_log<R>(R(1) + (in[0] - P[1]) / P[1]);
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// GhgForcing — crates/rscm-magicc/src/forcing/ghg.rs:122-125,164-279
+//   P: see include/rscm_b200.h (21 values, method first)
+// ---------------------------------------------------------------------------
+constexpr int GHG_FORCING_NP = 21;
+constexpr int GHG_FORCING_ND = 1;
+
+template <class R> __device__ __forceinline__ void ghg_forcing_prepare(const R *, R *D) { D[0] = R(0); }
+
+template <class R> __device__ __forceinline__ R ghg_overlap_f(R ch4, R n2o)
+{
+    const R mn = ch4 * n2o;
+    return R(0.47) * r_log<R>(R(1) + R(2.01e-5) * r_pow<R>(mn, R(0.75)) +
+                              R(5.31e-15) * ch4 * r_pow<R>(mn, R(1.52)));
+}
+
+template <class R>
+__device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *, const R *in, R *out, int)
+{
+    const R co2 = in[0], ch4 = in[1], n2o = in[2];
+    R co2_raw, ch4_raw, n2o_raw;
+    if (P[0] == R(0)) { // Ipcctar, ghg.rs:164-200
+        co2_raw = (P[4] / R(0.6931471805599453094172321)) * r_log<R>(co2 / P[1]);
+        ch4_raw = P[5] * (r_sqrt<R>(ch4) - r_sqrt<R>(P[2])) -
+                  (ghg_overlap_f<R>(ch4, P[3]) - ghg_overlap_f<R>(P[2], P[3]));
+        n2o_raw = P[6] * (r_sqrt<R>(n2o) - r_sqrt<R>(P[3])) -
+                  (ghg_overlap_f<R>(P[2], n2o) - ghg_overlap_f<R>(P[2], P[3]));
+    } else { // Olbl, ghg.rs:205-259
+        const R co2_pi = P[1], a1 = P[7], b1 = P[8], c1 = P[9], d1 = P[10];
+        const R delta = co2 - co2_pi;
+        const R n2o_overlap = c1 * r_sqrt<R>(n2o);
+        const R c_max = co2_pi - b1 / (R(2) * a1);
+        R alpha;
+        if (co2 >= c_max) alpha = -b1 * b1 / (R(4) * a1) + d1 + n2o_overlap;
+        else if (co2 <= co2_pi) alpha = d1 + n2o_overlap;
+        else alpha = a1 * delta * delta + b1 * delta + d1 + n2o_overlap;
+        co2_raw = alpha * r_log<R>(co2 / co2_pi);
+        const R s_ch4 = r_sqrt<R>(ch4), s_n2o = r_sqrt<R>(n2o), s_co2 = r_sqrt<R>(co2);
+        ch4_raw = (P[11] * s_ch4 + P[12] * s_n2o + P[13]) * (s_ch4 - r_sqrt<R>(P[2]));
+        n2o_raw = (P[14] * s_co2 + P[15] * s_n2o + P[16] * s_ch4 + P[17]) * (s_n2o - r_sqrt<R>(P[3]));
+    }
+    out[0] = co2_raw * P[18];
+    out[1] = ch4_raw * P[19];
+    out[2] = n2o_raw * P[20];
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// Schema aggregates — crates/rscm-core/src/schema.rs:760-806 (NaN contributors
+// are dropped; all-NaN -> NaN) and read-side grid aggregation
+// (state/aggregating.rs:162-177: weighted sum over non-NaN regions).
+// ---------------------------------------------------------------------------
+template <class R, int N>
+__device__ __forceinline__ R agg_sum(const R (&v)[N])
+{
+    R s = R(0);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (v[i] == v[i]) { s += v[i]; ++cnt; }
+    return cnt ? s : r_nan<R>();
+}
+
+template <class R, int N>
+__device__ __forceinline__ R agg_mean(const R (&v)[N])
+{
+    R s = R(0);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (v[i] == v[i]) { s += v[i]; ++cnt; }
+    return cnt ? s / R(cnt) : r_nan<R>();
+}
+
+template <class R, int N>
+__device__ __forceinline__ R agg_weighted(const R (&v)[N], const R (&w)[N])
+{
+    R s = R(0);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (v[i] == v[i]) { s += v[i] * w[i]; ++cnt; }
+    return cnt ? s : r_nan<R>();
+}
+
+// read transform FourBox/Hemispheric -> Scalar: NaN regions skipped, no renormalisation
+template <class R, int N>
+__device__ __forceinline__ R read_weighted(const R (&v)[N], const R (&w)[N])
+{
+    R s = R(0);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (v[i] == v[i]) s += v[i] * w[i];
+    return s;
+}
+
+} // namespace rscm_dev

@@ -1,0 +1,720 @@
+// engine.cu — C-ABI implementation of the B200 ensemble engine (include/rscm_b200.h).
+//
+// Host side: graph compile (graph.cpp) -> look the emitted program up in the
+// ahead-of-time registry (aot_programs.inc, generated at build time by
+// tools/gen_aot from the same emitter) -> launch the fused member-loop kernel
+// (kernel.cuh).  There is no CPU execution path in this library.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "graph.hpp"
+#include "kernel.cuh"
+
+using rscm_dev::KArgs;
+
+namespace {
+
+typedef cudaError_t (*launch_fn)(int dtype, bool write, bool logp, dim3 grid, size_t smem, cudaStream_t st,
+                                 const KArgs &a);
+
+struct AotEntry {
+    const char *name;
+    const char *signature;
+    launch_fn launch;
+};
+
+template <class Prog>
+cudaError_t launch_prog(int dtype, bool write, bool logp, dim3 grid, size_t smem, cudaStream_t st, const KArgs &a)
+{
+    using namespace rscm_dev;
+    const dim3 block(BLOCK);
+    if (dtype == 0) {
+        if (write && !logp) ensemble_kernel<double, Prog, true, false><<<grid, block, smem, st>>>(a);
+        else if (!write && logp) ensemble_kernel<double, Prog, false, true><<<grid, block, smem, st>>>(a);
+        else ensemble_kernel<double, Prog, true, true><<<grid, block, smem, st>>>(a);
+    } else {
+        if (write && !logp) ensemble_kernel<float, Prog, true, false><<<grid, block, smem, st>>>(a);
+        else if (!write && logp) ensemble_kernel<float, Prog, false, true><<<grid, block, smem, st>>>(a);
+        else ensemble_kernel<float, Prog, true, true><<<grid, block, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+#include "aot_programs.inc"
+
+thread_local std::string g_global_err;
+
+} // namespace
+
+struct rscm_b200_ensemble {
+    rscm::Graph g;
+    int dtype = 0;
+    int device = 0;
+    const AotEntry *prog = nullptr;
+    std::string err;
+    int Tpad = 0;
+
+    // bindings
+    int n_cols = 0;
+    std::vector<int> slot_col, init_col;
+    // output selection
+    std::vector<int> sel_vars;
+    int t_start = 0, t_stop = 0, t_step = 1, n_tsel = 0;
+    std::vector<int> out_base, out_tmul;
+    int64_t rows = 0;
+    // target / priors
+    int n_obs_rows = 0;
+    int obs_cell[rscm_dev::MAX_OBS_ROWS] = {0, 0, 0, 0};
+    int normalize = 0;
+    bool has_target = false;
+    int n_priors = 0;
+
+    // device scratch
+    double *d_exo = nullptr;
+    int64_t exo_capacity_S = 0;
+    int *d_nsub = nullptr;
+    double *d_obs = nullptr;
+    rscm_dev::PriorDev *d_priors = nullptr;
+    rscm_dev::BlockPartial *d_partials = nullptr;
+    int64_t partials_capacity = 0;
+    unsigned *d_ticket = nullptr;
+    int *d_row_off = nullptr, *d_row_stride = nullptr;
+    int64_t scen_stride = 0;
+    // host pipeline
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    double *d_params[2] = {nullptr, nullptr};
+    double *d_out[2] = {nullptr, nullptr};
+    unsigned char *d_status[2] = {nullptr, nullptr};
+    double *d_scen = nullptr;
+    double *d_logpost = nullptr;
+    rscm_dev::SummaryDev *d_summary = nullptr;
+    int64_t cap_params = 0, cap_out = 0, cap_status = 0, cap_scen = 0, cap_logpost = 0;
+
+    // stats
+    int64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    size_t ev_next = 0;
+    std::vector<char> ev_pending;
+    double kernel_ms_sum = 0.0;
+    int64_t kernel_ms_n = 0;
+};
+
+namespace {
+
+int fail(rscm_b200_ensemble *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    g_global_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(h, RSCM_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+void recompute_selection(rscm_b200_ensemble *h)
+{
+    const rscm::Graph &g = h->g;
+    h->out_base.assign(g.n_cells, -1);
+    h->out_tmul.assign(g.n_cells, 1);
+    h->n_tsel = 0;
+    for (int t = h->t_start; t < h->t_stop; t += h->t_step) ++h->n_tsel;
+    int64_t row = 0;
+    for (int v : h->sel_vars) {
+        const rscm::Variable &var = g.vars[v];
+        for (int r = 0; r < var.n_regions; ++r) {
+            h->out_base[var.cell0 + r] = static_cast<int>(row + r);
+            h->out_tmul[var.cell0 + r] = var.n_regions;
+        }
+        row += static_cast<int64_t>(h->n_tsel) * var.n_regions;
+    }
+    h->rows = row;
+}
+
+void harvest_event(rscm_b200_ensemble *h, size_t i)
+{
+    if (!h->ev_pending[i]) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->events[i].first, h->events[i].second) == cudaSuccess) {
+        h->kernel_ms_sum += ms;
+        h->kernel_ms_n += 1;
+    }
+    h->ev_pending[i] = 0;
+}
+
+size_t smem_bytes(const rscm_b200_ensemble *h, bool logp)
+{
+    size_t b = 16;
+    b += static_cast<size_t>(h->g.n_exo_rows) * h->Tpad * 8;
+    if (logp) b += static_cast<size_t>(2 * h->n_obs_rows) * h->Tpad * 8;
+    b += static_cast<size_t>(h->g.n_rk) * h->Tpad * 4;
+    return b;
+}
+
+// enqueue scenario packing + the fused kernel on `st`
+int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout, const double *d_scen, int64_t S,
+            double *d_out, unsigned char *d_status, double *d_logpost, rscm_dev::SummaryDev *d_summary, bool write,
+            bool logp, cudaStream_t st, bool pack)
+{
+    const rscm::Graph &g = h->g;
+    if (M <= 0) return fail(h, RSCM_B200_EINVAL, "M must be positive");
+    if (g.n_exo_rows > 0 && (S <= 0 || !d_scen)) return fail(h, RSCM_B200_EINVAL, "this graph needs scenarios for its exogenous variables");
+    if (g.n_exo_rows == 0 && S <= 0) S = 1;
+    if (S > 65535) return fail(h, RSCM_B200_EINVAL, "at most 65535 scenarios per call");
+    if (h->n_cols > 0 && !d_params) return fail(h, RSCM_B200_EINVAL, "parameter matrix required (columns are bound)");
+    if (logp && !h->has_target) return fail(h, RSCM_B200_EINVAL, "set a target before evaluating the log-posterior");
+
+    if (g.n_exo_rows > 0) {
+        if (S > h->exo_capacity_S) {
+            if (h->d_exo) cudaFree(h->d_exo);
+            h->d_exo = nullptr;
+            CU(cudaMalloc(&h->d_exo, static_cast<size_t>(S) * g.n_exo_rows * h->Tpad * 8));
+            h->exo_capacity_S = S;
+        }
+        if (pack) {
+            const long long total = S * g.n_exo_rows * static_cast<long long>(h->Tpad);
+            const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+            rscm_dev::pack_scenarios_kernel<<<blocks, 256, 0, st>>>(d_scen, h->d_exo, g.n_exo_rows, g.T, h->Tpad, S,
+                                                                   h->d_row_off, h->d_row_stride, h->scen_stride);
+            CU(cudaGetLastError());
+            h->launches++;
+        }
+    }
+
+    KArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.params = d_params;
+    a.M = M;
+    if (layout == 0) { a.ld_col = M; a.ld_mem = 1; } else { a.ld_col = 1; a.ld_mem = h->n_cols; }
+    a.n_cols = h->n_cols;
+    a.T = g.T;
+    a.Tpad = h->Tpad;
+    a.exo = h->d_exo;
+    a.nsub = h->d_nsub;
+    a.obs = h->d_obs;
+    a.n_exo_rows = g.n_exo_rows;
+    a.n_rk = g.n_rk;
+    a.n_obs_rows = logp ? h->n_obs_rows : 0;
+    a.normalize = h->normalize;
+    for (int j = 0; j < rscm_dev::MAX_OBS_ROWS; ++j) a.obs_cell[j] = h->obs_cell[j];
+    a.out = d_out;
+    a.runs = S * M;
+    a.status = d_status;
+    a.logpost = d_logpost;
+    a.priors = (logp && h->n_priors > 0) ? h->d_priors : nullptr;
+    a.t_start = h->t_start;
+    a.t_stop = h->t_stop;
+    a.t_step = h->t_step;
+    for (int i = 0; i < g.n_slots; ++i) { a.slot_col[i] = h->slot_col[i]; a.slot_def[i] = g.slot_default[i]; }
+    for (int c = 0; c < g.n_cells; ++c) {
+        a.init_col[c] = h->init_col[c];
+        const rscm::Variable &var = g.vars[g.cell_var[c]];
+        a.init_def[c] = var.has_initial ? var.initial : std::numeric_limits<double>::quiet_NaN();
+        a.out_base[c] = write ? h->out_base[c] : -1;
+        a.out_tmul[c] = h->out_tmul[c];
+    }
+    const dim3 grid(static_cast<unsigned>((M + rscm_dev::BLOCK - 1) / rscm_dev::BLOCK), static_cast<unsigned>(S));
+    if (logp && d_summary) {
+        const int64_t nb = static_cast<int64_t>(grid.x) * grid.y;
+        if (nb > h->partials_capacity) {
+            if (h->d_partials) cudaFree(h->d_partials);
+            h->d_partials = nullptr;
+            CU(cudaMalloc(&h->d_partials, static_cast<size_t>(nb) * sizeof(rscm_dev::BlockPartial)));
+            h->partials_capacity = nb;
+        }
+        a.partials = h->d_partials;
+        a.summary = d_summary;
+        a.ticket = h->d_ticket;
+    }
+
+    // CUDA-event timing of the fused kernel on its launch stream
+    size_t ei = h->ev_next;
+    if (h->events.size() < 64) {
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        h->events.push_back({e0, e1});
+        h->ev_pending.push_back(0);
+        ei = h->events.size() - 1;
+    } else {
+        if (h->ev_pending[ei]) {
+            cudaEventSynchronize(h->events[ei].second);
+            harvest_event(h, ei);
+        }
+    }
+    h->ev_next = (ei + 1) % 64;
+    CU(cudaEventRecord(h->events[ei].first, st));
+    cudaError_t e = h->prog->launch(h->dtype, write, logp, grid, smem_bytes(h, logp), st, a);
+    if (e != cudaSuccess) return fail(h, RSCM_B200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    CU(cudaEventRecord(h->events[ei].second, st));
+    h->ev_pending[ei] = 1;
+    h->launches++;
+    return RSCM_B200_OK;
+}
+
+template <class T> int ensure(rscm_b200_ensemble *h, T **p, int64_t *cap, int64_t need)
+{
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(reinterpret_cast<void **>(p), static_cast<size_t>(need) * sizeof(T)));
+    *cap = need;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int rscm_b200_abi_version(void) { return RSCM_B200_ABI_VERSION; }
+
+int rscm_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *rscm_b200_last_global_error(void) { return g_global_err.c_str(); }
+const char *rscm_b200_last_error(const rscm_b200_ensemble *h) { return h ? h->err.c_str() : g_global_err.c_str(); }
+
+int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemble **out)
+{
+    if (!desc || !out) return fail(nullptr, RSCM_B200_EINVAL, "null argument");
+    *out = nullptr;
+    rscm_b200_ensemble *h = new rscm_b200_ensemble();
+    std::string err;
+    if (!rscm::compile_graph(*desc, h->g, err)) {
+        delete h;
+        return fail(nullptr, RSCM_B200_EINVAL, err);
+    }
+    const rscm::Graph &g = h->g;
+    if (g.n_cells > rscm_dev::MAX_CELLS || g.n_slots > rscm_dev::MAX_SLOTS) {
+        delete h;
+        return fail(nullptr, RSCM_B200_EUNSUPPORTED, "graph exceeds the engine's cell/slot limits");
+    }
+    h->dtype = desc->compute_dtype ? 1 : 0;
+    for (const AotEntry &e : g_aot)
+        if (g.signature == e.signature) { h->prog = &e; break; }
+    if (!h->prog) {
+        delete h;
+        return fail(nullptr, RSCM_B200_EUNSUPPORTED,
+                    "no device program for this component graph (ahead-of-time registry miss); there is no CPU fallback");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        delete h;
+        return fail(nullptr, RSCM_B200_ENODEVICE, "no CUDA device available; the engine has no CPU fallback");
+    }
+    if (desc->device >= 0) {
+        if (desc->device >= ndev || cudaSetDevice(desc->device) != cudaSuccess) {
+            delete h;
+            return fail(nullptr, RSCM_B200_ENODEVICE, "cannot select the requested CUDA device");
+        }
+    }
+    cudaGetDevice(&h->device);
+    h->Tpad = (g.T + 3) & ~3;
+    h->slot_col.assign(g.n_slots, -1);
+    h->init_col.assign(g.n_cells, -1);
+    for (size_t v = 0; v < g.vars.size(); ++v) h->sel_vars.push_back(static_cast<int>(v));
+    h->t_start = 0;
+    h->t_stop = g.T;
+    h->t_step = 1;
+    recompute_selection(h);
+
+    // RK4 sub-step tables
+    if (g.n_rk > 0) {
+        std::vector<int> tab(static_cast<size_t>(g.n_rk) * h->Tpad, 0);
+        for (int r = 0; r < g.n_rk; ++r)
+            for (int t = 0; t < g.T; ++t) tab[static_cast<size_t>(r) * h->Tpad + t] = g.rk_nsub[r][t];
+        if (cudaMalloc(&h->d_nsub, tab.size() * sizeof(int)) != cudaSuccess ||
+            cudaMemcpy(h->d_nsub, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+            std::string m = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+            rscm_b200_ensemble_destroy(h);
+            return fail(nullptr, RSCM_B200_ECUDA, m);
+        }
+    }
+    // scenario row map: user layout [S][exo var][T][R] -> staged rows
+    if (g.n_exo_rows > 0) {
+        std::vector<int> off(g.n_exo_rows), stride(g.n_exo_rows);
+        int64_t base = 0;
+        int row = 0;
+        for (int v : g.exo_vars) {
+            const rscm::Variable &var = g.vars[v];
+            for (int r = 0; r < var.n_regions; ++r) {
+                off[row] = static_cast<int>(base + r);
+                stride[row] = var.n_regions;
+                ++row;
+            }
+            base += static_cast<int64_t>(g.T) * var.n_regions;
+        }
+        h->scen_stride = base;
+        cudaMalloc(&h->d_row_off, off.size() * sizeof(int));
+        cudaMalloc(&h->d_row_stride, off.size() * sizeof(int));
+        cudaMemcpy(h->d_row_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemcpy(h->d_row_stride, stride.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    cudaMalloc(&h->d_ticket, sizeof(unsigned));
+    cudaMemset(h->d_ticket, 0, sizeof(unsigned));
+    if (cudaGetLastError() != cudaSuccess) {
+        rscm_b200_ensemble_destroy(h);
+        return fail(nullptr, RSCM_B200_ECUDA, "device allocation failed");
+    }
+    *out = h;
+    return RSCM_B200_OK;
+}
+
+void rscm_b200_ensemble_destroy(rscm_b200_ensemble *h)
+{
+    if (!h) return;
+    cudaFree(h->d_exo); cudaFree(h->d_nsub); cudaFree(h->d_obs); cudaFree(h->d_priors); cudaFree(h->d_partials);
+    cudaFree(h->d_ticket); cudaFree(h->d_row_off); cudaFree(h->d_row_stride); cudaFree(h->d_scen);
+    cudaFree(h->d_logpost); cudaFree(h->d_summary);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->d_params[i]); cudaFree(h->d_out[i]); cudaFree(h->d_status[i]);
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    }
+    for (auto &e : h->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    cudaGetLastError();
+    delete h;
+}
+
+int rscm_b200_n_variables(const rscm_b200_ensemble *h) { return static_cast<int>(h->g.vars.size()); }
+const char *rscm_b200_variable_name(const rscm_b200_ensemble *h, int v)
+{
+    return (v >= 0 && v < static_cast<int>(h->g.vars.size())) ? h->g.vars[v].name.c_str() : nullptr;
+}
+int rscm_b200_variable_grid(const rscm_b200_ensemble *h, int v) { return h->g.vars[v].grid; }
+int rscm_b200_variable_is_endogenous(const rscm_b200_ensemble *h, int v) { return h->g.vars[v].endogenous ? 1 : 0; }
+int rscm_b200_variable_index(const rscm_b200_ensemble *h, const char *name) { return h->g.find_var(name); }
+int rscm_b200_n_exogenous(const rscm_b200_ensemble *h) { return static_cast<int>(h->g.exo_vars.size()); }
+int rscm_b200_exogenous_variable(const rscm_b200_ensemble *h, int i) { return h->g.exo_vars[i]; }
+int rscm_b200_n_nodes(const rscm_b200_ensemble *h) { return static_cast<int>(h->g.nodes.size()); }
+int rscm_b200_execution_order(const rscm_b200_ensemble *h, int *order, int capacity)
+{
+    const int n = static_cast<int>(h->g.order.size());
+    for (int i = 0; i < n && i < capacity; ++i) order[i] = h->g.order[i];
+    return n;
+}
+int rscm_b200_variable_source(const rscm_b200_ensemble *h, int component, const char *variable)
+{
+    if (component < 0 || component >= static_cast<int>(h->g.nodes.size())) return -1;
+    const rscm::Node &n = h->g.nodes[component];
+    const int v = h->g.find_var(variable);
+    for (size_t i = 0; i < n.in_var.size(); ++i)
+        if (n.in_var[i] == v) return n.in_src[i];
+    return -1;
+}
+const char *rscm_b200_program_signature(const rscm_b200_ensemble *h) { return h->g.signature.c_str(); }
+int rscm_b200_time_index(const rscm_b200_ensemble *h, double time) { return rscm::time_index_for(h->g, time); }
+
+int rscm_b200_bind_parameters(rscm_b200_ensemble *h, int n_bindings, const char *const *slots, const int32_t *columns,
+                              int n_columns)
+{
+    if (!h) return RSCM_B200_EINVAL;
+    std::vector<int> slot_col(h->g.n_slots, -1), init_col(h->g.n_cells, -1);
+    for (int i = 0; i < n_bindings; ++i) {
+        if (columns[i] < 0 || columns[i] >= n_columns) return fail(h, RSCM_B200_EINVAL, "binding column out of range");
+        std::string err;
+        const int s = h->g.resolve_slot(slots[i], err);
+        if (s == -1000000000) return fail(h, RSCM_B200_EINVAL, err);
+        if (s >= 0) slot_col[s] = columns[i];
+        else {
+            const int cell0 = -(s + 1);
+            const rscm::Variable &var = h->g.vars[h->g.cell_var[cell0]];
+            // a scalar initial value is broadcast to every region (builder.rs:797-803,821-824)
+            for (int r = 0; r < var.n_regions; ++r) init_col[cell0 + r] = columns[i];
+        }
+    }
+    h->slot_col = slot_col;
+    h->init_col = init_col;
+    h->n_cols = n_columns;
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_select_outputs(rscm_b200_ensemble *h, int n_vars, const int32_t *vars, int32_t t_start, int32_t t_stop,
+                             int32_t t_step)
+{
+    if (!h) return RSCM_B200_EINVAL;
+    if (t_step < 1 || t_start < 0 || t_stop > h->g.T || t_start > t_stop) return fail(h, RSCM_B200_EINVAL, "bad time selection");
+    std::vector<int> sel;
+    for (int i = 0; i < n_vars; ++i) {
+        if (vars[i] < 0 || vars[i] >= static_cast<int>(h->g.vars.size())) return fail(h, RSCM_B200_EINVAL, "bad variable index");
+        for (int s : sel) if (s == vars[i]) return fail(h, RSCM_B200_EINVAL, "variable selected twice");
+        sel.push_back(vars[i]);
+    }
+    h->sel_vars = sel;
+    h->t_start = t_start;
+    h->t_stop = t_stop;
+    h->t_step = t_step;
+    recompute_selection(h);
+    return RSCM_B200_OK;
+}
+
+int64_t rscm_b200_output_rows(const rscm_b200_ensemble *h) { return h->rows; }
+
+int rscm_b200_set_target(rscm_b200_ensemble *h, const rscm_b200_obs *obs, int64_t n_obs, int normalize)
+{
+    if (!h) return RSCM_B200_EINVAL;
+    const rscm::Graph &g = h->g;
+    // dense tables: one row per observed variable (a repeated (variable, time) opens another row)
+    std::vector<int> row_var;
+    std::vector<std::vector<double>> val, sig;
+    for (int64_t i = 0; i < n_obs; ++i) {
+        const rscm_b200_obs &o = obs[i];
+        if (o.variable < 0 || o.variable >= static_cast<int>(g.vars.size())) return fail(h, RSCM_B200_EINVAL, "observation: bad variable");
+        if (g.vars[o.variable].grid != RSCM_B200_SCALAR)
+            return fail(h, RSCM_B200_EINVAL, "observation on a grid variable (reference: 'Grid variables not yet supported')");
+        if (!(o.sigma > 0.0)) return fail(h, RSCM_B200_EINVAL, "observation uncertainty must be positive");
+        if (o.time_index < 0 || o.time_index >= g.T) return fail(h, RSCM_B200_EINVAL, "observation time index out of range (reference: missing time => Err)");
+        int row = -1;
+        for (size_t r = 0; r < row_var.size(); ++r)
+            if (row_var[r] == o.variable && sig[r][o.time_index] == 0.0) { row = static_cast<int>(r); break; }
+        if (row < 0) {
+            if (row_var.size() >= static_cast<size_t>(rscm_dev::MAX_OBS_ROWS))
+                return fail(h, RSCM_B200_EUNSUPPORTED, "too many observed variables / duplicate observation times");
+            row_var.push_back(o.variable);
+            val.push_back(std::vector<double>(h->Tpad, 0.0));
+            sig.push_back(std::vector<double>(h->Tpad, 0.0));
+            row = static_cast<int>(row_var.size()) - 1;
+        }
+        val[row][o.time_index] = o.value;
+        sig[row][o.time_index] = o.sigma;
+    }
+    h->n_obs_rows = static_cast<int>(row_var.size());
+    for (int r = 0; r < h->n_obs_rows; ++r) h->obs_cell[r] = g.vars[row_var[r]].cell0;
+    h->normalize = normalize ? 1 : 0;
+    if (h->d_obs) cudaFree(h->d_obs);
+    h->d_obs = nullptr;
+    if (h->n_obs_rows > 0) {
+        std::vector<double> flat;
+        for (auto &v : val) flat.insert(flat.end(), v.begin(), v.end());
+        for (auto &s : sig) flat.insert(flat.end(), s.begin(), s.end());
+        CU(cudaMalloc(&h->d_obs, flat.size() * sizeof(double)));
+        CU(cudaMemcpy(h->d_obs, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->has_target = true;
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_set_priors(rscm_b200_ensemble *h, const rscm_b200_prior *priors, int n_columns)
+{
+    if (!h) return RSCM_B200_EINVAL;
+    if (h->d_priors) cudaFree(h->d_priors);
+    h->d_priors = nullptr;
+    h->n_priors = 0;
+    if (n_columns <= 0) return RSCM_B200_OK;
+    if (n_columns != h->n_cols) return fail(h, RSCM_B200_EINVAL, "one prior per bound parameter column required");
+    std::vector<rscm_dev::PriorDev> p(n_columns);
+    for (int i = 0; i < n_columns; ++i) {
+        p[i].kind = priors[i].kind; p[i].pad = 0;
+        p[i].a = priors[i].a; p[i].b = priors[i].b; p[i].low = priors[i].low; p[i].high = priors[i].high;
+    }
+    CU(cudaMalloc(&h->d_priors, p.size() * sizeof(rscm_dev::PriorDev)));
+    CU(cudaMemcpy(h->d_priors, p.data(), p.size() * sizeof(rscm_dev::PriorDev), cudaMemcpyHostToDevice));
+    h->n_priors = n_columns;
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_run_device(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
+                         const double *scenarios, int64_t S, double *out, uint8_t *status, void *stream)
+{
+    if (!h || !out) return fail(h, RSCM_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    return enqueue(h, params, M, params_layout, scenarios, S, out, status, nullptr, nullptr, true, false,
+                   static_cast<cudaStream_t>(stream), true);
+}
+
+int rscm_b200_logpost_device(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
+                             const double *scenarios, int64_t S, double *logpost,
+                             rscm_b200_logpost_summary *summary, void *stream)
+{
+    if (!h || !logpost) return fail(h, RSCM_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    static_assert(sizeof(rscm_b200_logpost_summary) == sizeof(rscm_dev::SummaryDev), "summary layout");
+    return enqueue(h, params, M, params_layout, scenarios, S, nullptr, nullptr, logpost,
+                   reinterpret_cast<rscm_dev::SummaryDev *>(summary), false, true, static_cast<cudaStream_t>(stream), true);
+}
+
+int rscm_b200_run_host(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
+                       const double *scenarios, int64_t S, double *out, uint8_t *status)
+{
+    if (!h || !out) return fail(h, RSCM_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    const rscm::Graph &g = h->g;
+    if (M <= 0) return fail(h, RSCM_B200_EINVAL, "M must be positive");
+    if (g.n_exo_rows == 0 && S <= 0) S = 1;
+    if (g.n_exo_rows > 0 && (S <= 0 || !scenarios)) return fail(h, RSCM_B200_EINVAL, "this graph needs scenarios for its exogenous variables");
+    for (int i = 0; i < 2; ++i)
+        if (!h->streams[i]) CU(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    // scenarios: one H2D + one pack, shared by all chunks
+    if (g.n_exo_rows > 0) {
+        if (ensure(h, &h->d_scen, &h->cap_scen, S * h->scen_stride)) return RSCM_B200_ECUDA;
+        CU(cudaMemcpyAsync(h->d_scen, scenarios, static_cast<size_t>(S) * h->scen_stride * 8, cudaMemcpyHostToDevice, h->streams[0]));
+    }
+    // chunk size: bound each device output buffer to ~1 GiB and keep >= 4 chunks in flight for overlap
+    const int64_t bytes_per_member = std::max<int64_t>(1, h->rows * S * 8);
+    int64_t Mc = std::max<int64_t>(rscm_dev::BLOCK, (int64_t(1) << 30) / bytes_per_member);
+    Mc = std::min(Mc, std::max<int64_t>(rscm_dev::BLOCK, (M + 3) / 4));
+    Mc = (Mc + rscm_dev::BLOCK - 1) / rscm_dev::BLOCK * rscm_dev::BLOCK;
+    Mc = std::min(Mc, M);
+    // capacities are shared between the two pipeline buffers: allocate both explicitly
+    {
+        const int64_t need_p = std::max<int64_t>(1, Mc * std::max(1, h->n_cols));
+        const int64_t need_o = std::max<int64_t>(1, h->rows * S * Mc);
+        const int64_t need_s = std::max<int64_t>(1, S * Mc);
+        if (need_p > h->cap_params || need_o > h->cap_out || need_s > h->cap_status) {
+            for (int i = 0; i < 2; ++i) {
+                cudaFree(h->d_params[i]); cudaFree(h->d_out[i]); cudaFree(h->d_status[i]);
+                h->d_params[i] = nullptr; h->d_out[i] = nullptr; h->d_status[i] = nullptr;
+                CU(cudaMalloc(&h->d_params[i], static_cast<size_t>(need_p) * 8));
+                CU(cudaMalloc(&h->d_out[i], static_cast<size_t>(need_o) * 8));
+                CU(cudaMalloc(&h->d_status[i], static_cast<size_t>(need_s)));
+            }
+            h->cap_params = need_p; h->cap_out = need_o; h->cap_status = need_s;
+        }
+    }
+    cudaEvent_t scen_ready;
+    CU(cudaEventCreateWithFlags(&scen_ready, cudaEventDisableTiming));
+    bool first = true;
+    int rc = RSCM_B200_OK;
+    int k = 0;
+    for (int64_t m0 = 0; m0 < M && rc == RSCM_B200_OK; m0 += Mc, ++k) {
+        const int64_t mc = std::min(Mc, M - m0);
+        const int b = k & 1;
+        cudaStream_t st = h->streams[b];
+        if (!first) CU(cudaStreamWaitEvent(st, scen_ready, 0));
+        if (h->n_cols > 0) {
+            if (params_layout == 0)
+                CU(cudaMemcpy2DAsync(h->d_params[b], static_cast<size_t>(mc) * 8, params + m0, static_cast<size_t>(M) * 8,
+                                     static_cast<size_t>(mc) * 8, h->n_cols, cudaMemcpyHostToDevice, st));
+            else
+                CU(cudaMemcpyAsync(h->d_params[b], params + m0 * h->n_cols, static_cast<size_t>(mc) * h->n_cols * 8,
+                                   cudaMemcpyHostToDevice, st));
+        }
+        rc = enqueue(h, h->d_params[b], mc, params_layout, h->d_scen, S, h->d_out[b], status ? h->d_status[b] : nullptr,
+                     nullptr, nullptr, true, false, st, first);
+        if (rc != RSCM_B200_OK) break;
+        if (first) { CU(cudaEventRecord(scen_ready, st)); first = false; }
+        // device chunk [rows][S][mc] -> host [rows][S][M] columns m0..m0+mc
+        CU(cudaMemcpy2DAsync(out + m0, static_cast<size_t>(M) * 8, h->d_out[b], static_cast<size_t>(mc) * 8,
+                             static_cast<size_t>(mc) * 8, static_cast<size_t>(h->rows * S), cudaMemcpyDeviceToHost, st));
+        if (status)
+            CU(cudaMemcpy2DAsync(status + m0, static_cast<size_t>(M), h->d_status[b], static_cast<size_t>(mc),
+                                 static_cast<size_t>(mc), static_cast<size_t>(S), cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
+    cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
+    cudaEventDestroy(scen_ready);
+    if (rc != RSCM_B200_OK) return rc;
+    if (e0 != cudaSuccess || e1 != cudaSuccess)
+        return fail(h, RSCM_B200_ECUDA, std::string("pipeline: ") + cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_logpost_host(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
+                           const double *scenarios, int64_t S, double *logpost, rscm_b200_logpost_summary *summary)
+{
+    if (!h || !logpost) return fail(h, RSCM_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    const rscm::Graph &g = h->g;
+    if (M <= 0) return fail(h, RSCM_B200_EINVAL, "M must be positive");
+    if (g.n_exo_rows == 0 && S <= 0) S = 1;
+    if (g.n_exo_rows > 0 && (S <= 0 || !scenarios)) return fail(h, RSCM_B200_EINVAL, "this graph needs scenarios for its exogenous variables");
+    if (!h->streams[0]) CU(cudaStreamCreateWithFlags(&h->streams[0], cudaStreamNonBlocking));
+    cudaStream_t st = h->streams[0];
+    if (g.n_exo_rows > 0) {
+        if (ensure(h, &h->d_scen, &h->cap_scen, S * h->scen_stride)) return RSCM_B200_ECUDA;
+        CU(cudaMemcpyAsync(h->d_scen, scenarios, static_cast<size_t>(S) * h->scen_stride * 8, cudaMemcpyHostToDevice, st));
+    }
+    const int64_t need_p = std::max<int64_t>(1, M * std::max(1, h->n_cols));
+    if (need_p > h->cap_params) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->d_params[i]); h->d_params[i] = nullptr;
+            CU(cudaMalloc(&h->d_params[i], static_cast<size_t>(need_p) * 8));
+        }
+        h->cap_params = need_p;
+    }
+    if (ensure(h, &h->d_logpost, &h->cap_logpost, S * M)) return RSCM_B200_ECUDA;
+    if (!h->d_summary) CU(cudaMalloc(&h->d_summary, sizeof(rscm_dev::SummaryDev)));
+    if (h->n_cols > 0)
+        CU(cudaMemcpyAsync(h->d_params[0], params, static_cast<size_t>(M) * h->n_cols * 8, cudaMemcpyHostToDevice, st));
+    int rc = enqueue(h, h->d_params[0], M, params_layout, h->d_scen, S, nullptr, nullptr, h->d_logpost,
+                     summary ? h->d_summary : nullptr, false, true, st, true);
+    if (rc != RSCM_B200_OK) return rc;
+    CU(cudaMemcpyAsync(logpost, h->d_logpost, static_cast<size_t>(S) * M * 8, cudaMemcpyDeviceToHost, st));
+    if (summary) CU(cudaMemcpyAsync(summary, h->d_summary, sizeof(rscm_dev::SummaryDev), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return RSCM_B200_OK;
+}
+
+int64_t rscm_b200_launch_count(const rscm_b200_ensemble *h) { return h ? h->launches : 0; }
+
+double rscm_b200_kernel_ms(rscm_b200_ensemble *h, int reset)
+{
+    if (!h) return 0.0;
+    for (size_t i = 0; i < h->events.size(); ++i) {
+        if (!h->ev_pending[i]) continue;
+        cudaEventSynchronize(h->events[i].second);
+        harvest_event(h, i);
+    }
+    const double avg = h->kernel_ms_n ? h->kernel_ms_sum / static_cast<double>(h->kernel_ms_n) : 0.0;
+    if (reset) { h->kernel_ms_sum = 0.0; h->kernel_ms_n = 0; }
+    return avg;
+}
+
+int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops)
+{
+    rscm_b200_ensemble *h = nullptr;
+    if (!tflops) return fail(nullptr, RSCM_B200_EINVAL, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, RSCM_B200_ENODEVICE, "no CUDA device available");
+    }
+    if (device >= 0) CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaGetDeviceProperties(&prop, dev));
+    void *sink = nullptr;
+    CU(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double best = 0.0;
+    int iters = 2000;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(cudaEventRecord(e0));
+        if (dtype == 0) rscm_dev::fma_peak_kernel<double><<<blocks, threads>>>(static_cast<double *>(sink), iters, 1.0);
+        else rscm_dev::fma_peak_kernel<float><<<blocks, threads>>>(static_cast<float *>(sink), iters, 1.0f);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 16.0 * 8.0 * iters * static_cast<double>(blocks) * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        if (ms < 20.f) iters *= 4;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops = best;
+    return RSCM_B200_OK;
+}
+
+} // extern "C"

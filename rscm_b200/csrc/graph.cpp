@@ -1,0 +1,542 @@
+// graph.cpp — host graph compiler (see graph.hpp).
+#include "graph.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <sstream>
+
+namespace rscm {
+
+// ---------------------------------------------------------------------------
+// Static descriptor tables: the output of the reference's #[derive(ComponentIO)]
+// (crates/rscm-macros/src/lib.rs:356-678) restated per kind.  Order of defs =
+// inputs, outputs, states (lib.rs:630-636).
+// ---------------------------------------------------------------------------
+static const std::vector<KindInfo> &kinds()
+{
+    static const std::vector<KindInfo> k = {
+        {RSCM_B200_TWO_LAYER, "TwoLayer", "two_layer",
+         // crates/rscm-two-layer/src/component.rs:147-154
+         {{"Effective Radiative Forcing", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Surface Temperature", REQ_STATE, RSCM_B200_SCALAR},
+          {"Deep Ocean Temperature", REQ_STATE, RSCM_B200_SCALAR}},
+         {"lambda0", "a", "efficacy", "eta", "heat_capacity_surface", "heat_capacity_deep"},
+         3, -1, {1, 1, 1, 1, 1, 1}},
+        {RSCM_B200_CARBON_CYCLE, "CarbonCycle", "carbon_cycle",
+         // crates/rscm-components/src/components/carbon_cycle.rs:62-72
+         {{"Emissions|CO2|Anthropogenic", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Surface Temperature", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Atmospheric Concentration|CO2", REQ_STATE, RSCM_B200_SCALAR},
+          {"Cumulative Emissions|CO2", REQ_STATE, RSCM_B200_SCALAR},
+          {"Cumulative Land Uptake", REQ_STATE, RSCM_B200_SCALAR}},
+         {"tau", "conc_pi", "alpha_temperature", "step_size"},
+         1, 3, {1, 1, 1, 0}},
+        {RSCM_B200_CO2_ERF, "CO2ERF", "co2_erf",
+         // crates/rscm-components/src/components/co2_erf.rs:36-44
+         {{"Atmospheric Concentration|CO2", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|CO2", REQ_OUTPUT, RSCM_B200_SCALAR}},
+         {"erf_2xco2", "conc_pi"},
+         1, -2, {1, 1}},
+        {RSCM_B200_GHG_FORCING, "GhgForcing", "ghg_forcing",
+         // crates/rscm-magicc/src/forcing/ghg.rs (derive block at top of file)
+         {{"Atmospheric Concentration|CO2", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Atmospheric Concentration|CH4", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Atmospheric Concentration|N2O", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|CO2", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|CH4", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|N2O", REQ_OUTPUT, RSCM_B200_SCALAR}},
+         {"method", "co2_pi", "ch4_pi", "n2o_pi", "delq2xco2", "ch4_radeff", "n2o_radeff",
+          "olbl_co2_a1", "olbl_co2_b1", "olbl_co2_c1", "olbl_co2_d1", "olbl_ch4_a3", "olbl_ch4_b3",
+          "olbl_ch4_d3", "olbl_n2o_a2", "olbl_n2o_b2", "olbl_n2o_c2", "olbl_n2o_d2", "adjust_co2",
+          "adjust_ch4", "adjust_n2o"},
+         1, -2, {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}},
+    };
+    return k;
+}
+
+const KindInfo *kind_info(int kind)
+{
+    for (const auto &k : kinds())
+        if (k.kind == kind) return &k;
+    return nullptr;
+}
+
+static int grid_regions(int grid)
+{
+    return grid == RSCM_B200_FOUR_BOX ? 4 : (grid == RSCM_B200_HEMISPHERIC ? 2 : 1);
+}
+
+int Graph::find_var(const std::string &name) const
+{
+    for (size_t i = 0; i < vars.size(); ++i)
+        if (vars[i].name == name) return static_cast<int>(i);
+    return -1;
+}
+
+// ode_solvers Rk4::integrate: n = ceil((x_end - x)/h) steps of constant h, x += h
+// each step; then get_last_step asserts y.len() > 1 and |x_last - t_next| < 5e-3.
+int rk4_substeps(double t0, double t1, double h)
+{
+    const double nd = std::ceil((t1 - t0) / h);
+    if (!(nd >= 1.0) || nd > 32000.0) return -1;
+    const int n = static_cast<int>(nd);
+    double x = t0;
+    for (int i = 0; i < n; ++i) x = x + h;
+    if (!(std::fabs(x - t1) < 5e-3)) return -1;
+    return n;
+}
+
+int time_index_for(const Graph &g, double time)
+{
+    char key[64], k2[64];
+    std::snprintf(key, sizeof key, "%.6f", time);
+    int found = -1;
+    for (int i = 0; i < g.T; ++i) {
+        std::snprintf(k2, sizeof k2, "%.6f", g.bounds[i]);
+        if (!std::strcmp(key, k2)) found = i; // HashMap insert: the later duplicate wins
+    }
+    return found;
+}
+
+static std::string lit(double v)
+{
+    char b[64];
+    std::snprintf(b, sizeof b, "R(%.17g)", v);
+    return b;
+}
+
+// ---------------------------------------------------------------------------
+// emit: the component graph as a device `Prog` body
+// ---------------------------------------------------------------------------
+static std::string cell_ref(bool at_end, int cell)
+{
+    std::ostringstream s;
+    s << (at_end ? "nxt[" : "cur[") << cell << "]";
+    return s.str();
+}
+
+// expression reading input `i` (region r of the component's view) of node n
+static std::string input_expr(const Graph &g, const Node &n, int i, int r, bool at_end, std::ostringstream &pre,
+                              int &tmp_id)
+{
+    const Variable &var = g.vars[n.in_var[i]];
+    const int want = n.in_grid[i];
+    std::string e;
+    if (want == var.grid) {
+        e = cell_ref(at_end, var.cell0 + r);
+    } else if (var.grid == RSCM_B200_FOUR_BOX && want == RSCM_B200_SCALAR) {
+        // AggregatingFourBoxWindow::aggregate — state/aggregating.rs:162-177
+        const int id = tmp_id++;
+        pre << "        const R rv" << id << "[4] = {" << cell_ref(at_end, var.cell0) << ", " << cell_ref(at_end, var.cell0 + 1)
+            << ", " << cell_ref(at_end, var.cell0 + 2) << ", " << cell_ref(at_end, var.cell0 + 3) << "};\n";
+        pre << "        const R rw" << id << "[4] = {" << lit(g.w_fourbox[0]) << ", " << lit(g.w_fourbox[1]) << ", "
+            << lit(g.w_fourbox[2]) << ", " << lit(g.w_fourbox[3]) << "};\n";
+        std::ostringstream s;
+        s << "rscm_dev::read_weighted<R, 4>(rv" << id << ", rw" << id << ")";
+        e = s.str();
+    } else if (var.grid == RSCM_B200_FOUR_BOX && want == RSCM_B200_HEMISPHERIC) {
+        // state/aggregating.rs:611-618
+        std::ostringstream s;
+        s << "((" << cell_ref(at_end, var.cell0 + 2 * r) << " + " << cell_ref(at_end, var.cell0 + 2 * r + 1) << ") / R(2))";
+        e = s.str();
+    } else { // Hemispheric -> Scalar
+        const int id = tmp_id++;
+        pre << "        const R rv" << id << "[2] = {" << cell_ref(at_end, var.cell0) << ", " << cell_ref(at_end, var.cell0 + 1) << "};\n";
+        pre << "        const R rw" << id << "[2] = {" << lit(g.w_hemi[0]) << ", " << lit(g.w_hemi[1]) << "};\n";
+        std::ostringstream s;
+        s << "rscm_dev::read_weighted<R, 2>(rv" << id << ", rw" << id << ")";
+        e = s.str();
+    }
+    if (n.in_factor[i] != 1.0) e = "(" + e + " * " + lit(n.in_factor[i]) + ")";
+    return e;
+}
+
+static void emit_program(Graph &g)
+{
+    std::ostringstream o;
+    o << "    static constexpr int NC = " << g.n_cells << ";\n";
+    o << "    static constexpr int NP = " << g.n_slots << ";\n";
+    o << "    static constexpr int ND = " << g.n_derived << ";\n";
+    o << "    __host__ __device__ static constexpr int exo_row(int c) { return ";
+    for (int c = 0; c < g.n_cells; ++c) {
+        const Variable &v = g.vars[g.cell_var[c]];
+        if (v.exo_row0 >= 0) o << "c == " << c << " ? " << (v.exo_row0 + g.cell_region[c]) << " : ";
+    }
+    o << "-1; }\n";
+    o << "    __host__ __device__ static constexpr bool endogenous(int c) { return ";
+    for (int c = 0; c < g.n_cells; ++c)
+        if (g.vars[g.cell_var[c]].endogenous) o << "c == " << c << " || ";
+    o << "false; }\n";
+    o << "    template <class R> __device__ __forceinline__ static void prepare(const R *P, R *D) {\n";
+    o << "        (void)P; (void)D;\n";
+    for (size_t ni = 0; ni < g.nodes.size(); ++ni) {
+        const Node &n = g.nodes[ni];
+        if (n.kind == KIND_AGGREGATOR) continue;
+        const KindInfo *k = kind_info(n.kind);
+        o << "        rscm_dev::" << k->dev_name << "_prepare<R>(P + " << n.param_base << ", D + " << n.derived_base << ");\n";
+    }
+    o << "    }\n";
+    o << "    template <class R> __device__ __forceinline__ static void step(const R *P, const R *D, const R *cur, R *nxt,\n"
+         "                                                                  const int *s_nsub, int Tpad, int N, unsigned &fail) {\n";
+    o << "        (void)P; (void)D; (void)cur; (void)s_nsub; (void)Tpad; (void)N; (void)fail;\n";
+    int tmp_id = 0;
+    for (int ni : g.order) {
+        const Node &n = g.nodes[ni];
+        o << "      { // node " << ni << "\n";
+        std::ostringstream pre;
+        if (n.kind == KIND_AGGREGATOR) {
+            // AggregatorComponent::solve — schema.rs:874-951: contributors read at_end
+            const int R = grid_regions(n.agg_grid);
+            const int nc = static_cast<int>(n.in_var.size());
+            std::ostringstream body;
+            for (int r = 0; r < R; ++r) {
+                body << "        { const R av[" << nc << "] = {";
+                for (int i = 0; i < nc; ++i) body << (i ? ", " : "") << input_expr(g, n, i, r, true, pre, tmp_id);
+                body << "};\n";
+                const int oc = g.vars[n.out_var[0]].cell0 + r;
+                if (n.agg_op == RSCM_B200_AGG_SUM) body << "          nxt[" << oc << "] = rscm_dev::agg_sum<R, " << nc << ">(av); }\n";
+                else if (n.agg_op == RSCM_B200_AGG_MEAN) body << "          nxt[" << oc << "] = rscm_dev::agg_mean<R, " << nc << ">(av); }\n";
+                else {
+                    body << "          const R aw[" << nc << "] = {";
+                    for (int i = 0; i < nc; ++i) body << (i ? ", " : "") << lit(n.agg_w[i]);
+                    body << "};\n          nxt[" << oc << "] = rscm_dev::agg_weighted<R, " << nc << ">(av, aw); }\n";
+                }
+            }
+            o << pre.str() << body.str();
+        } else {
+            const KindInfo *k = kind_info(n.kind);
+            std::vector<std::string> in_exprs;
+            for (size_t i = 0; i < n.in_var.size(); ++i) {
+                const int Rc = grid_regions(n.in_grid[i]);
+                // get(): UpstreamOutput -> at_end (always in range during run), else at_start
+                // (state/windows.rs:229-234); state inputs are read with at_start.
+                const bool at_end = n.in_src[i] == RSCM_B200_SRC_UPSTREAM;
+                for (int r = 0; r < Rc; ++r) in_exprs.push_back(input_expr(g, n, static_cast<int>(i), r, at_end, pre, tmp_id));
+            }
+            int n_out_vals = 0;
+            for (size_t i = 0; i < n.out_var.size(); ++i) n_out_vals += grid_regions(n.out_grid[i]);
+            o << pre.str();
+            o << "        const R in[" << (in_exprs.empty() ? 1 : in_exprs.size()) << "] = {";
+            for (size_t i = 0; i < in_exprs.size(); ++i) o << (i ? ", " : "") << in_exprs[i];
+            if (in_exprs.empty()) o << "R(0)";
+            o << "};\n";
+            o << "        R out[" << n_out_vals << "];\n";
+            o << "        if (rscm_dev::" << k->dev_name << "_solve<R>(P + " << n.param_base << ", D + " << n.derived_base
+              << ", in, out, ";
+            if (n.rk_table >= 0) o << "s_nsub[" << n.rk_table << " * Tpad + N]";
+            else o << "0";
+            o << ")) {\n";
+            int pos = 0;
+            for (size_t i = 0; i < n.out_var.size(); ++i) {
+                const Variable &var = g.vars[n.out_var[i]];
+                const int Rc = grid_regions(n.out_grid[i]);
+                if (n.out_grid[i] == var.grid) {
+                    for (int r = 0; r < Rc; ++r) o << "            nxt[" << (var.cell0 + r) << "] = out[" << (pos + r) << "];\n";
+                } else if (n.out_grid[i] == RSCM_B200_FOUR_BOX && var.grid == RSCM_B200_SCALAR) {
+                    // write-side aggregation — model/transformations.rs:31-128
+                    o << "            nxt[" << var.cell0 << "] = out[" << pos << "] * " << lit(g.w_fourbox[0]) << " + out[" << pos + 1
+                      << "] * " << lit(g.w_fourbox[1]) << " + out[" << pos + 2 << "] * " << lit(g.w_fourbox[2]) << " + out["
+                      << pos + 3 << "] * " << lit(g.w_fourbox[3]) << ";\n";
+                } else if (n.out_grid[i] == RSCM_B200_FOUR_BOX && var.grid == RSCM_B200_HEMISPHERIC) {
+                    const double wn = g.w_fourbox[0] + g.w_fourbox[1], ws = g.w_fourbox[2] + g.w_fourbox[3];
+                    o << "            nxt[" << var.cell0 << "] = (out[" << pos << "] * " << lit(g.w_fourbox[0]) << " + out[" << pos + 1
+                      << "] * " << lit(g.w_fourbox[1]) << ") / " << lit(wn) << ";\n";
+                    o << "            nxt[" << var.cell0 + 1 << "] = (out[" << pos + 2 << "] * " << lit(g.w_fourbox[2]) << " + out["
+                      << pos + 3 << "] * " << lit(g.w_fourbox[3]) << ") / " << lit(ws) << ";\n";
+                } else { // Hemispheric -> Scalar
+                    o << "            nxt[" << var.cell0 << "] = out[" << pos << "] * " << lit(g.w_hemi[0]) << " + out[" << pos + 1
+                      << "] * " << lit(g.w_hemi[1]) << ";\n";
+                }
+                pos += Rc;
+            }
+            o << "        } else { fail |= 1u; }\n";
+        }
+        o << "      }\n";
+    }
+    o << "    }\n";
+    g.program_source = o.str();
+    g.signature = g.program_source;
+}
+
+// ---------------------------------------------------------------------------
+// compile_graph — ModelBuilder::build restated (builder.rs:418-860)
+// ---------------------------------------------------------------------------
+bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
+{
+    if (d.abi_version != RSCM_B200_ABI_VERSION) { err = "ABI version mismatch"; return false; }
+    if (d.n_times < 2 || !d.time_bounds) { err = "time axis with at least 2 points required"; return false; }
+    if (d.n_components < 1 || !d.components) { err = "at least one component required"; return false; }
+    g = Graph();
+    g.T = d.n_times;
+    g.bounds.assign(d.time_bounds, d.time_bounds + d.n_times + 1);
+    if (d.four_box_weights) std::memcpy(g.w_fourbox, d.four_box_weights, sizeof g.w_fourbox);
+    if (d.hemispheric_weights) std::memcpy(g.w_hemi, d.hemispheric_weights, sizeof g.w_hemi);
+
+    std::vector<std::string> agg_names;
+    for (int i = 0; i < d.n_aggregates; ++i) agg_names.push_back(d.aggregates[i].name);
+    auto is_agg = [&](const std::string &n) {
+        for (auto &a : agg_names) if (a == n) return true;
+        return false;
+    };
+    if (d.n_aggregates > 0 && !d.has_schema) { err = "aggregates require a schema"; return false; }
+
+    auto add_var = [&](const char *name, int grid, int req) {
+        int v = g.find_var(name);
+        if (v >= 0) return v; // the first definition wins (model/validation.rs:30-107)
+        Variable var;
+        var.name = name;
+        var.grid = grid;
+        var.req = req;
+        g.vars.push_back(var);
+        return static_cast<int>(g.vars.size()) - 1;
+    };
+
+    // graph node ids: 0 = NullComponent root, node i -> i + 1
+    std::vector<std::pair<int, int>> edges;
+    std::map<int, int> producer; // `endogenous`: var -> graph node id
+    std::vector<std::pair<int, int>> pending; // (graph node, var) aggregate deps (builder.rs:441)
+
+    for (int ci = 0; ci < d.n_components; ++ci) {
+        const rscm_b200_component_desc &cd = d.components[ci];
+        const KindInfo *k = kind_info(cd.kind);
+        if (!k) {
+            err = "component kind " + std::to_string(cd.kind) + " has no device implementation (no CPU fallback)";
+            return false;
+        }
+        if (cd.n_params != static_cast<int>(k->param_names.size()) || !cd.params) {
+            err = std::string("wrong parameter count for ") + k->type_name;
+            return false;
+        }
+        Node n;
+        n.kind = cd.kind;
+        n.params.assign(cd.params, cd.params + cd.n_params);
+        const int gnode = ci + 1;
+        bool has_dep = false;
+        // requires: classification (builder.rs:465-488) and edges (:490-519), inputs() order
+        for (const VarDef &def : k->defs) {
+            if (def.req == REQ_OUTPUT) continue;
+            const int v = add_var(def.name, def.grid, def.req);
+            int src;
+            if (def.req == REQ_STATE) src = RSCM_B200_SRC_OWN_STATE;
+            else if (producer.count(v)) src = RSCM_B200_SRC_UPSTREAM;
+            else if (is_agg(def.name)) src = RSCM_B200_SRC_UPSTREAM;
+            else src = RSCM_B200_SRC_EXOGENOUS;
+            n.in_var.push_back(v);
+            n.in_src.push_back(src);
+            n.in_grid.push_back(def.grid);
+            n.in_factor.push_back(1.0);
+            if (producer.count(v)) { edges.push_back({producer[v], gnode}); has_dep = true; }
+            else if (is_agg(def.name)) { pending.push_back({gnode, v}); has_dep = true; }
+            else g.vars[v].in_exogenous_list = true;
+        }
+        if (!has_dep) edges.push_back({0, gnode}); // builder.rs:521-531
+        // provides (builder.rs:533-560), outputs() order
+        for (const VarDef &def : k->defs) {
+            if (def.req == REQ_INPUT) continue;
+            const int v = add_var(def.name, def.grid, def.req);
+            n.out_var.push_back(v);
+            n.out_grid.push_back(def.grid);
+            if (producer.count(v)) edges.push_back({producer[v], gnode});
+            producer[v] = gnode;
+        }
+        g.nodes.push_back(n);
+    }
+    g.n_user = d.n_components;
+
+    for (int i = 0; i < d.n_unit_factors; ++i) {
+        const rscm_b200_unit_factor &uf = d.unit_factors[i];
+        if (uf.component < 0 || uf.component >= g.n_user) { err = "unit factor: bad component index"; return false; }
+        const int v = g.find_var(uf.variable);
+        Node &n = g.nodes[uf.component];
+        for (size_t j = 0; j < n.in_var.size(); ++j)
+            if (n.in_var[j] == v) n.in_factor[j] = uf.factor;
+    }
+
+    if (d.has_schema) {
+        // schema is the source of truth for the storage grid (builder.rs:593-630)
+        for (int s = 0; s < d.n_schema_variables; ++s) {
+            const rscm_b200_schema_variable &sv = d.schema_variables[s];
+            int v = g.find_var(sv.name);
+            if (v < 0) {
+                v = add_var(sv.name, sv.grid, REQ_INPUT);
+                g.vars[v].in_exogenous_list = true;
+            } else if (g.vars[v].grid != sv.grid) {
+                g.vars[v].grid = sv.grid;
+                if (!producer.count(v)) g.vars[v].in_exogenous_list = true;
+            }
+        }
+        // aggregators (builder.rs:631-700)
+        for (int ai = 0; ai < d.n_aggregates; ++ai) {
+            const rscm_b200_aggregate_desc &ad = d.aggregates[ai];
+            Node n;
+            n.kind = KIND_AGGREGATOR;
+            n.agg_name = ad.name;
+            n.agg_op = ad.op;
+            n.agg_grid = ad.grid;
+            const int gnode = static_cast<int>(g.nodes.size()) + 1;
+            bool has_dep = false;
+            if (ad.n_contributors < 1) { err = "aggregate without contributors"; return false; }
+            if (ad.op == RSCM_B200_AGG_WEIGHTED && !ad.weights) { err = "weighted aggregate without weights"; return false; }
+            for (int i = 0; i < ad.n_contributors; ++i) {
+                int v = g.find_var(ad.contributors[i]);
+                if (v < 0) {
+                    v = add_var(ad.contributors[i], ad.grid, REQ_INPUT);
+                    g.vars[v].in_exogenous_list = true;
+                }
+                n.agg_contrib.push_back(ad.contributors[i]);
+                n.agg_w.push_back(ad.weights ? ad.weights[i] : 1.0);
+                n.in_var.push_back(v);
+                n.in_src.push_back(RSCM_B200_SRC_EXOGENOUS); // unused: contributors are read at_end explicitly
+                n.in_grid.push_back(ad.grid);
+                n.in_factor.push_back(1.0);
+                if (producer.count(v)) { edges.push_back({producer[v], gnode}); has_dep = true; }
+            }
+            if (!has_dep) edges.push_back({0, gnode});
+            const int v = add_var(ad.name, ad.grid, REQ_OUTPUT);
+            g.vars[v].grid = ad.grid;
+            n.out_var.push_back(v);
+            n.out_grid.push_back(ad.grid);
+            producer[v] = gnode;
+            g.nodes.push_back(n);
+        }
+        for (auto &p : pending)
+            if (producer.count(p.second)) edges.push_back({producer[p.second], p.first});
+    }
+
+    // supported transforms only run fine -> coarse
+    for (const Node &n : g.nodes) {
+        for (size_t i = 0; i < n.in_var.size(); ++i) {
+            const int sg = g.vars[n.in_var[i]].grid, wg = n.in_grid[i];
+            if (sg == wg || sg == RSCM_B200_FOUR_BOX || (sg == RSCM_B200_HEMISPHERIC && wg == RSCM_B200_SCALAR)) continue;
+            err = "variable '" + g.vars[n.in_var[i]].name + "': read transform coarse -> fine is not defined";
+            return false;
+        }
+        for (size_t i = 0; i < n.out_var.size(); ++i) {
+            const int sg = g.vars[n.out_var[i]].grid, cg = n.out_grid[i];
+            if (sg == cg || cg == RSCM_B200_FOUR_BOX || (cg == RSCM_B200_HEMISPHERIC && sg == RSCM_B200_SCALAR)) continue;
+            err = "variable '" + g.vars[n.out_var[i]].name + "': write transform coarse -> fine is not defined";
+            return false;
+        }
+    }
+
+    // variables: initial values, endogenous flag, cells, staged rows
+    for (size_t v = 0; v < g.vars.size(); ++v) {
+        Variable &var = g.vars[v];
+        var.n_regions = grid_regions(var.grid);
+        var.endogenous = producer.count(static_cast<int>(v)) > 0;
+        for (int i = 0; i < d.n_initial_values; ++i)
+            if (var.name == d.initial_values[i].name) { var.has_initial = true; var.initial = d.initial_values[i].value; }
+        if (var.req == REQ_STATE && !var.has_initial) { // builder.rs:703-716
+            err = "missing initial value for state variable '" + var.name + "'";
+            return false;
+        }
+        var.cell0 = g.n_cells;
+        for (int r = 0; r < var.n_regions; ++r) { g.cell_var.push_back(static_cast<int>(v)); g.cell_region.push_back(r); }
+        g.n_cells += var.n_regions;
+        if (!var.endogenous) {
+            var.exo_index = static_cast<int>(g.exo_vars.size());
+            var.exo_row0 = g.n_exo_rows;
+            g.exo_vars.push_back(static_cast<int>(v));
+            g.n_exo_rows += var.n_regions;
+        }
+    }
+
+    // execution order: petgraph Bfs from the root; Graph::neighbors walks outgoing
+    // edges most-recently-added first (model/runtime.rs:504-510)
+    {
+        const int total = static_cast<int>(g.nodes.size()) + 1;
+        std::vector<char> seen(total, 0);
+        std::deque<int> q;
+        q.push_back(0);
+        seen[0] = 1;
+        while (!q.empty()) {
+            const int u = q.front();
+            q.pop_front();
+            if (u != 0) g.order.push_back(u - 1);
+            for (int e = static_cast<int>(edges.size()) - 1; e >= 0; --e) {
+                if (edges[e].first != u) continue;
+                const int w = edges[e].second;
+                if (!seen[w]) { seen[w] = 1; q.push_back(w); }
+            }
+        }
+        // cycle check (builder.rs:563)
+        std::vector<int> indeg(total, 0);
+        std::vector<char> removed(total, 0);
+        for (auto &e : edges) indeg[e.second]++;
+        int done = 0;
+        for (bool progressed = true; progressed;) {
+            progressed = false;
+            for (int u = 0; u < total; ++u) {
+                if (removed[u] || indeg[u]) continue;
+                removed[u] = 1; ++done; progressed = true;
+                for (auto &e : edges) if (e.first == u) indeg[e.second]--;
+            }
+        }
+        if (done != total) { err = "component graph contains a cycle"; return false; }
+        // The device program executes nodes in exactly this BFS order with `nxt` cells
+        // NaN until written, so a consumer that the BFS schedules before its producer
+        // reads NaN at N+1 just as it does in the reference (no topological re-sort).
+    }
+
+    // parameter / derived slots, RK4 tables
+    for (size_t ni = 0; ni < g.nodes.size(); ++ni) {
+        Node &n = g.nodes[ni];
+        if (n.kind == KIND_AGGREGATOR) continue;
+        const KindInfo *k = kind_info(n.kind);
+        n.param_base = g.n_slots;
+        n.derived_base = g.n_derived;
+        for (size_t p = 0; p < n.params.size(); ++p) {
+            g.slot_default.push_back(n.params[p]);
+            g.slot_bindable.push_back(k->bindable[p]);
+        }
+        g.n_slots += static_cast<int>(n.params.size());
+        g.n_derived += k->n_derived;
+        if (k->rk_step_param != -2) {
+            const double h = k->rk_step_param >= 0 ? n.params[k->rk_step_param] : 0.1;
+            n.rk_table = g.n_rk++;
+            std::vector<int> tab(g.T, 0);
+            for (int N = 0; N + 1 < g.T; ++N) tab[N] = rk4_substeps(g.bounds[N], g.bounds[N + 1], h);
+            g.rk_nsub.push_back(tab);
+        }
+    }
+    emit_program(g);
+    return true;
+}
+
+int Graph::resolve_slot(const std::string &slot, std::string &err) const
+{
+    if (slot.rfind("initial:", 0) == 0) {
+        const int v = find_var(slot.substr(8));
+        if (v < 0) { err = "unknown variable in '" + slot + "'"; return -1000000000; }
+        return -(vars[v].cell0) - 1;
+    }
+    const size_t dot = slot.rfind('.');
+    if (dot == std::string::npos) { err = "bad slot '" + slot + "'"; return -1000000000; }
+    std::string type = slot.substr(0, dot), field = slot.substr(dot + 1);
+    int want_index = -1;
+    const size_t hash = type.find('#');
+    if (hash != std::string::npos) {
+        want_index = std::atoi(type.c_str() + hash + 1);
+        type = type.substr(0, hash);
+    }
+    for (int ni = 0; ni < n_user; ++ni) {
+        const Node &n = nodes[ni];
+        const KindInfo *k = kind_info(n.kind);
+        if (type != k->type_name) continue;
+        if (want_index >= 0 && want_index != ni) continue;
+        for (size_t p = 0; p < k->param_names.size(); ++p) {
+            if (field != k->param_names[p]) continue;
+            if (!k->bindable[p]) { err = "parameter '" + slot + "' cannot vary per member"; return -1000000000; }
+            return n.param_base + static_cast<int>(p);
+        }
+        err = "unknown field in '" + slot + "'";
+        return -1000000000;
+    }
+    err = "no component matches '" + slot + "'";
+    return -1000000000;
+}
+
+} // namespace rscm

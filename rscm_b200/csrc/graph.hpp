@@ -1,0 +1,105 @@
+// graph.hpp — host-side graph compiler of the ensemble engine.
+//
+// Reproduces, once per ensemble, what the reference does once per member:
+// ModelBuilder::build (crates/rscm-core/src/model/builder.rs:418-860) — variable
+// table, insertion-order-dependent VariableSource classification, dependency
+// edges, schema aggregators — and the petgraph BFS execution order
+// (model/runtime.rs:504-510).  The result is lowered to (a) flat tables the
+// kernel arguments are filled from and (b) the source text of a `Prog` struct:
+// the component graph as straight-line device code (see kernel.cuh).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/rscm_b200.h"
+
+namespace rscm {
+
+enum Req { REQ_INPUT = 0, REQ_OUTPUT = 1, REQ_STATE = 2 };
+constexpr int KIND_AGGREGATOR = 4;
+
+struct VarDef {
+    const char *name;
+    int req;
+    int grid;
+};
+
+struct KindInfo {
+    int kind;
+    const char *type_name; // Rust struct name (Debug prefix used by the reference for lookups)
+    const char *dev_name;  // prefix of <dev_name>_prepare / <dev_name>_solve in components.cuh
+    std::vector<VarDef> defs;
+    std::vector<const char *> param_names;
+    int n_derived;
+    int rk_step_param; // index of the RK4 step-size parameter, -1: fixed 0.1, -2: no RK4
+    std::vector<int> bindable; // 1 if the parameter may be bound to a member column
+};
+
+const KindInfo *kind_info(int kind);
+
+struct Variable {
+    std::string name;
+    int grid = 0;
+    int n_regions = 1;
+    int req = REQ_INPUT;
+    bool endogenous = false;
+    bool in_exogenous_list = false;
+    bool has_initial = false;
+    double initial = 0.0;
+    int cell0 = 0;   // first storage cell
+    int exo_index = -1; // position among exogenous variables, -1 if endogenous
+    int exo_row0 = -1;  // first staged row
+};
+
+struct Node {
+    int kind = 0;
+    std::vector<double> params;
+    int param_base = 0;   // first parameter slot
+    int derived_base = 0; // first derived-constant slot
+    int rk_table = -1;    // row of the sub-step table
+    std::vector<int> in_var, in_src, in_grid;
+    std::vector<double> in_factor;
+    std::vector<int> out_var, out_grid;
+    // aggregator
+    std::string agg_name;
+    int agg_op = 0, agg_grid = 0;
+    std::vector<std::string> agg_contrib;
+    std::vector<double> agg_w;
+};
+
+struct Graph {
+    std::vector<Variable> vars;
+    std::vector<Node> nodes; // components in insertion order, then aggregators
+    int n_user = 0;
+    std::vector<int> order;     // node ids in execution order
+    std::vector<int> exo_vars;  // variable ids, scenario order
+    int n_cells = 0, n_slots = 0, n_derived = 0, n_exo_rows = 0, n_rk = 0;
+    std::vector<double> slot_default;
+    std::vector<int> slot_bindable;
+    std::vector<int> cell_var, cell_region;
+    int T = 0;
+    std::vector<double> bounds;
+    double w_fourbox[4] = {0.25, 0.25, 0.25, 0.25};
+    double w_hemi[2] = {0.5, 0.5};
+    std::vector<std::vector<int>> rk_nsub; // [n_rk][T]
+    std::string program_source;            // emitted Prog body (without the struct name)
+    std::string signature;                 // canonical key = hash-free text of the program
+
+    int find_var(const std::string &name) const;
+    // slot id for "<Type>.<field>", "<Type>#i.<field>"; cell id for "initial:<var>" (returned as -(cell)-1); -1e9 if unknown
+    int resolve_slot(const std::string &slot, std::string &err) const;
+};
+
+// Builds the graph; returns false and fills err on failure.
+bool compile_graph(const rscm_b200_graph_desc &desc, Graph &g, std::string &err);
+
+// RK4 sub-step count per time step and get_last_step check
+// (ode_solvers 0.6.1 Rk4::integrate; crates/rscm-core/src/ivp/mod.rs:90-102):
+// returns n >= 1, or -1 when the reference would panic.
+int rk4_substeps(double t0, double t1, double h);
+
+// "{:.6}" key equality (crates/rscm-calibrate/src/likelihood.rs:40-42)
+int time_index_for(const Graph &g, double time);
+
+} // namespace rscm

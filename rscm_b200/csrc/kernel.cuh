@@ -1,0 +1,428 @@
+// kernel.cuh — the fused per-member time-loop kernel (sm_100a).
+//
+// One thread = one run (member m of scenario s = blockIdx.y).  The compiled
+// component graph arrives as a `Prog` struct emitted by the host graph compiler
+// (graph.cpp: emit_program): straight-line calls into components.cuh with literal
+// cell / parameter indices, so every parameter, derived constant and state cell
+// is a register.  There are no per-step launches: the whole `Model::run` loop
+// (crates/rscm-core/src/model/runtime.rs:515-527) is the `for N` loop below.
+//
+// Per block, the scenario's exogenous series, the RK4 sub-step tables and the
+// observation tables are staged once into shared memory with TMA bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx); parameter loads
+// are issued while the copies are in flight.
+//
+// Outputs are written structure-of-arrays, out[row][run] with run = s*M + m, so a
+// warp's store of one (variable, time) row is one contiguous 256 B segment;
+// stores carry the streaming (.cs) hint because outputs are never re-read.
+#pragma once
+#include <cstdint>
+#include "components.cuh"
+
+namespace rscm_dev {
+
+constexpr int MAX_SLOTS = 96;   // component parameter slots per program
+constexpr int MAX_CELLS = 48;   // scalar storage cells (variables x regions)
+constexpr int MAX_OBS_ROWS = 4; // dense observation tables (one per observed variable)
+constexpr int BLOCK = 128;
+
+struct PriorDev {
+    int kind;
+    int pad;
+    double a, b, low, high;
+};
+
+struct BlockPartial {
+    double max_lp;
+    long long argmax;
+    double sum_finite;
+    long long n_finite;
+};
+
+struct SummaryDev {
+    double max_logpost;
+    long long argmax;
+    double sum_finite;
+    long long n_finite;
+    long long n_runs;
+};
+
+struct KArgs {
+    // parameter matrix: element (col j, member m) = params[j*ld_col + m*ld_mem]
+    const double *params;
+    long long M;
+    long long ld_col, ld_mem;
+    int n_cols;
+    int T, Tpad;
+    // staged tables (global, 16-byte aligned, sizes multiples of 16 B)
+    const double *exo;   // [S][n_exo_rows][Tpad]
+    const int *nsub;     // [n_rk][Tpad]   RK4 sub-steps per step; <0: get_last_step would assert
+    const double *obs;   // [2][n_obs_rows][Tpad]: values then sigmas (sigma<=0: no observation)
+    int n_exo_rows, n_rk, n_obs_rows;
+    int normalize;
+    int obs_cell[MAX_OBS_ROWS];
+    // outputs
+    double *out;
+    long long runs;
+    unsigned char *status;
+    double *logpost;
+    const PriorDev *priors; // [n_cols] or null
+    BlockPartial *partials; // [gridDim.x*gridDim.y] or null
+    SummaryDev *summary;
+    unsigned int *ticket;
+    int t_start, t_stop, t_step; // selected time indices: t_start + k*t_step < t_stop
+    // slot tables (compile-time indexed after unrolling -> constant-bank loads)
+    int slot_col[MAX_SLOTS];
+    double slot_def[MAX_SLOTS];
+    int init_col[MAX_CELLS];
+    double init_def[MAX_CELLS];
+    int out_base[MAX_CELLS]; // first output row of this cell (var row0 + region) or -1
+    int out_tmul[MAX_CELLS]; // regions of the cell's variable
+};
+
+// ---- mbarrier / TMA bulk-copy primitives (PTX) -----------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
+
+// Distribution::ln_pdf — crates/rscm-calibrate/src/distribution.rs:157-163,256-259,353-360,490-497
+__device__ inline double prior_ln_pdf(const PriorDev &p, double x)
+{
+    const double ln_2pi_half = 0.5 * 1.8378770664093454835606594728112;
+    int kind = p.kind;
+    if (kind >= 4) {
+        if (x < p.low || x > p.high) return -CUDART_INF;
+        kind = (kind == 4) ? 2 : (kind == 5 ? 3 : 1);
+    }
+    if (kind == 1) {
+        if (x < p.a || x > p.b) return -CUDART_INF;
+        return -log(p.b - p.a);
+    }
+    if (kind == 2) {
+        const double z = (x - p.a) / p.b;
+        return -0.5 * z * z - log(p.b) - ln_2pi_half;
+    }
+    if (kind == 3) {
+        if (x <= 0.0) return -CUDART_INF;
+        const double ln_x = log(x);
+        const double z = (ln_x - p.a) / p.b;
+        return -0.5 * z * z - ln_x - log(p.b) - ln_2pi_half;
+    }
+    return 0.0;
+}
+
+// GaussianLikelihood::observation_ln_likelihood — likelihood.rs:186-199
+template <class R, int NC>
+__device__ __forceinline__ void obs_accumulate(const KArgs &a, const double *s_obs, int tidx,
+                                               const R (&vals)[NC], double (&ll)[MAX_OBS_ROWS], bool &bad)
+{
+#pragma unroll
+    for (int j = 0; j < MAX_OBS_ROWS; ++j) {
+        if (j < a.n_obs_rows) {
+            const double sig = s_obs[(a.n_obs_rows + j) * a.Tpad + tidx];
+            if (sig > 0.0) { // block-uniform
+                const double val = s_obs[j * a.Tpad + tidx];
+                double model = 0.0;
+                const int cell = a.obs_cell[j];
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (c == cell) model = static_cast<double>(vals[c]);
+                // missing (NaN) or non-finite model value => Err => -inf (likelihood.rs:209-221)
+                if (!(fabs(model) <= 1.7976931348623157e308)) bad = true;
+                const double residual = val - model;
+                double l = -0.5 * ((residual * residual) / (sig * sig));
+                if (a.normalize) {
+                    l -= 0.5 * 1.8378770664093454835606594728112;
+                    l -= log(sig);
+                }
+                ll[j] += l;
+            }
+        }
+    }
+}
+
+template <class R, class Prog, bool WRITE, bool LOGP>
+__global__ void __launch_bounds__(BLOCK) ensemble_kernel(const __grid_constant__ KArgs a)
+{
+    constexpr int NC = Prog::NC;
+    constexpr int NP = Prog::NP;
+    constexpr int ND = Prog::ND;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
+    double *s_exo = reinterpret_cast<double *>(smem + 16);
+    double *s_obs = s_exo + static_cast<size_t>(a.n_exo_rows) * a.Tpad;
+    int *s_nsub = reinterpret_cast<int *>(s_obs + static_cast<size_t>(2 * a.n_obs_rows) * a.Tpad);
+
+    const unsigned exo_bytes = static_cast<unsigned>(a.n_exo_rows) * a.Tpad * 8u;
+    const unsigned obs_bytes = LOGP ? static_cast<unsigned>(2 * a.n_obs_rows) * a.Tpad * 8u : 0u;
+    const unsigned nsub_bytes = static_cast<unsigned>(a.n_rk) * a.Tpad * 4u;
+    const unsigned total_bytes = exo_bytes + obs_bytes + nsub_bytes;
+
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && total_bytes) {
+        mbar_expect_tx(bar, total_bytes);
+        if (exo_bytes)
+            tma_bulk_g2s(s_exo, a.exo + static_cast<size_t>(blockIdx.y) * a.n_exo_rows * a.Tpad, exo_bytes, bar);
+        if (obs_bytes) tma_bulk_g2s(s_obs, a.obs, obs_bytes, bar);
+        if (nsub_bytes) tma_bulk_g2s(s_nsub, a.nsub, nsub_bytes, bar);
+    }
+
+    // ---- per-member parameters (coalesced SoA loads overlap the bulk copies) ----
+    const long long m_raw = static_cast<long long>(blockIdx.x) * BLOCK + threadIdx.x;
+    const bool active = m_raw < a.M;
+    const long long m = active ? m_raw : a.M - 1;
+    const long long run = static_cast<long long>(blockIdx.y) * a.M + m;
+    const double *pm = a.params + m * a.ld_mem;
+
+    R P[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        P[i] = a.slot_col[i] >= 0 ? static_cast<R>(__ldg(pm + a.slot_col[i] * a.ld_col)) : static_cast<R>(a.slot_def[i]);
+    R D[ND > 0 ? ND : 1];
+    Prog::template prepare<R>(P, D);
+
+    double lp = 0.0;
+    if (LOGP && a.priors) {
+        // ParameterSet::log_prior — parameter_set.rs:255-270
+        for (int j = 0; j < a.n_cols; ++j) lp += prior_ln_pdf(a.priors[j], __ldg(pm + j * a.ld_col));
+    }
+
+    R cur[NC], nxt[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        cur[c] = a.init_col[c] >= 0 ? static_cast<R>(__ldg(pm + a.init_col[c] * a.ld_col)) : static_cast<R>(a.init_def[c]);
+        nxt[c] = r_nan<R>();
+    }
+
+    if (total_bytes) mbar_wait(bar, 0);
+
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        if (Prog::exo_row(c) >= 0) cur[c] = static_cast<R>(s_exo[Prog::exo_row(c) * a.Tpad]);
+
+    double ll[MAX_OBS_ROWS] = {0.0, 0.0, 0.0, 0.0};
+    bool bad = false;
+    unsigned fail = 0;
+
+    // index 0: initial values / exogenous echo (model/builder.rs:771-781)
+    int tsel = 0; // next selected-time ordinal
+    int tnext = a.t_start;
+    if (WRITE) {
+        if (tnext == 0 && tnext < a.t_stop) {
+            if (active) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (a.out_base[c] >= 0)
+                        store_stream(a.out + static_cast<long long>(a.out_base[c]) * a.runs + run,
+                                     static_cast<double>(cur[c]));
+            }
+            tsel = 1;
+            tnext += a.t_step;
+        }
+    }
+    if (LOGP) obs_accumulate<R, NC>(a, s_obs, 0, cur, ll, bad);
+
+    const int T = a.T;
+    for (int N = 0; N < T - 1; ++N) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(s_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
+            else nxt[c] = r_nan<R>();
+        }
+        Prog::template step<R>(P, D, cur, nxt, s_nsub, a.Tpad, N, fail);
+
+        if (WRITE) {
+            if (N + 1 == tnext && tnext < a.t_stop) { // block-uniform
+                if (active) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+                        if (a.out_base[c] >= 0)
+                            store_stream(a.out + (static_cast<long long>(a.out_base[c]) +
+                                                  static_cast<long long>(tsel) * a.out_tmul[c]) * a.runs + run,
+                                         static_cast<double>(nxt[c]));
+                }
+                ++tsel;
+                tnext += a.t_step;
+            }
+        }
+        if (LOGP) obs_accumulate<R, NC>(a, s_obs, N + 1, nxt, ll, bad);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cur[c] = nxt[c];
+    }
+
+    if (a.status && active) {
+        bool nonfinite = false;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (Prog::endogenous(c) && !(fabs(static_cast<double>(cur[c])) <= 1.7976931348623157e308)) nonfinite = true;
+        a.status[run] = static_cast<unsigned char>((fail ? 1u : 0u) | (nonfinite ? 2u : 0u));
+    }
+
+    if (LOGP) {
+        // EnsembleSampler::log_posterior_batch — sampler/ensemble.rs:143-178
+        double total = 0.0;
+#pragma unroll
+        for (int j = 0; j < MAX_OBS_ROWS; ++j)
+            if (j < a.n_obs_rows) total += ll[j];
+        double post = lp + total;
+        if (bad || !(fabs(lp) <= 1.7976931348623157e308)) post = -CUDART_INF;
+        if (active) a.logpost[run] = post;
+
+        if (a.summary) {
+            // warp-shuffle + block reduction of the ensemble summary
+            const bool fin = active && (fabs(post) <= 1.7976931348623157e308);
+            double vmax = fin ? post : -CUDART_INF;
+            long long amax = fin ? run : -1;
+            double vsum = fin ? post : 0.0;
+            long long cnt = fin ? 1 : 0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double omax = __shfl_down_sync(0xffffffffu, vmax, off);
+                const long long oarg = __shfl_down_sync(0xffffffffu, amax, off);
+                if (omax > vmax || (omax == vmax && oarg >= 0 && (amax < 0 || oarg < amax))) { vmax = omax; amax = oarg; }
+                vsum += __shfl_down_sync(0xffffffffu, vsum, off);
+                cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+            }
+            __shared__ BlockPartial s_part[BLOCK / 32];
+            __shared__ bool s_last;
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (lane == 0) s_part[warp] = BlockPartial{vmax, amax, vsum, cnt};
+            __syncthreads();
+            const unsigned nblocks = gridDim.x * gridDim.y;
+            const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+            if (threadIdx.x == 0) {
+                BlockPartial r = s_part[0];
+                for (int w = 1; w < BLOCK / 32; ++w) {
+                    const BlockPartial o = s_part[w];
+                    if (o.max_lp > r.max_lp || (o.max_lp == r.max_lp && o.argmax >= 0 && (r.argmax < 0 || o.argmax < r.argmax))) {
+                        r.max_lp = o.max_lp; r.argmax = o.argmax;
+                    }
+                    r.sum_finite += o.sum_finite;
+                    r.n_finite += o.n_finite;
+                }
+                a.partials[bid] = r;
+                __threadfence();
+                const unsigned t = atomicAdd(a.ticket, 1u);
+                s_last = (t == nblocks - 1);
+            }
+            __syncthreads();
+            if (s_last) {
+                // last block: deterministic tree over the per-block partials
+                __threadfence();
+                double bmax = -CUDART_INF, bsum = 0.0;
+                long long barg = -1, bcnt = 0;
+                for (unsigned i = threadIdx.x; i < nblocks; i += BLOCK) {
+                    const BlockPartial o = a.partials[i];
+                    if (o.max_lp > bmax || (o.max_lp == bmax && o.argmax >= 0 && (barg < 0 || o.argmax < barg))) { bmax = o.max_lp; barg = o.argmax; }
+                    bsum += o.sum_finite;
+                    bcnt += o.n_finite;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double omax = __shfl_down_sync(0xffffffffu, bmax, off);
+                    const long long oarg = __shfl_down_sync(0xffffffffu, barg, off);
+                    if (omax > bmax || (omax == bmax && oarg >= 0 && (barg < 0 || oarg < barg))) { bmax = omax; barg = oarg; }
+                    bsum += __shfl_down_sync(0xffffffffu, bsum, off);
+                    bcnt += __shfl_down_sync(0xffffffffu, bcnt, off);
+                }
+                if (lane == 0) s_part[warp] = BlockPartial{bmax, barg, bsum, bcnt};
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    BlockPartial r = s_part[0];
+                    for (int w = 1; w < BLOCK / 32; ++w) {
+                        const BlockPartial o = s_part[w];
+                        if (o.max_lp > r.max_lp || (o.max_lp == r.max_lp && o.argmax >= 0 && (r.argmax < 0 || o.argmax < r.argmax))) {
+                            r.max_lp = o.max_lp; r.argmax = o.argmax;
+                        }
+                        r.sum_finite += o.sum_finite;
+                        r.n_finite += o.n_finite;
+                    }
+                    a.summary->max_logpost = r.max_lp;
+                    a.summary->argmax = r.argmax;
+                    a.summary->sum_finite = r.sum_finite;
+                    a.summary->n_finite = r.n_finite;
+                    a.summary->n_runs = a.runs;
+                    *a.ticket = 0u; // re-arm for the next launch
+                }
+            }
+        }
+    }
+}
+
+// scenario packing: user layout [S][var][T][R_v]  ->  staged rows [S][cell][Tpad]
+__global__ void pack_scenarios_kernel(const double *__restrict__ src, double *__restrict__ dst, int n_rows,
+                                      int T, int Tpad, long long S, const int *__restrict__ row_src_off,
+                                      const int *__restrict__ row_src_stride, long long src_scen_stride)
+{
+    const long long total = S * n_rows * static_cast<long long>(Tpad);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(i % Tpad);
+        const long long rs = i / Tpad;
+        const int row = static_cast<int>(rs % n_rows);
+        const long long s = rs / n_rows;
+        double v = 0.0;
+        if (t < T) v = src[s * src_scen_stride + row_src_off[row] + static_cast<long long>(t) * row_src_stride[row]];
+        dst[i] = v;
+    }
+}
+
+// params transpose [M][n_cols] -> [n_cols][M] is not needed: the kernel takes strides.
+
+// FMA-pipe saturating micro-benchmark (roofline denominator for the FP64/FP32 bound)
+template <class R>
+__global__ void __launch_bounds__(256) fma_peak_kernel(R *sink, int iters, R seed)
+{
+    R a0 = seed + R(threadIdx.x), a1 = a0 + R(1), a2 = a0 + R(2), a3 = a0 + R(3);
+    R a4 = a0 + R(4), a5 = a0 + R(5), a6 = a0 + R(6), a7 = a0 + R(7);
+    const R b = R(0.999999), c = R(1e-6);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+            a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+        }
+    }
+    const R s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == R(-1)) sink[0] = s; // never true; keeps the chain live
+}
+
+} // namespace rscm_dev
