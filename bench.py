@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — ensemble member-years/second on BASELINE.json's coupled carbon+two-layer config.
+
+    python bench.py --gpus N --steps K --warmup W             (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle port)
+
+A "step" = one pass of the hot path over the whole batch: M members x S scenarios x 350 years
+(`ModelRunner::run_batch` of the coupled graph).  One JSON line on stdout (rank 0).
+
+  value        device-resident throughput: params + scenarios already in HBM, all 7 output series
+               written to HBM ([rows][runs] fp64), CUDA-event timed per step, L2 flushed between steps
+  e2e          the same workload through the host C-ABI call (rscm_b200_run_host): parameters from
+               pinned host memory, the `output_variables` the runner was asked for copied back to
+               pinned host memory, copies inside the timed region
+  roofline     FP64-pipe roofline of the fused kernel: algorithmic flop (1710 per
+               member-year) / kernel time vs the DFMA peak measured in this run; HBM-write roofline beside it
+  cpu_baseline the CPU oracle (port of the reference arithmetic) on a bounded sample, rank 0, N = 1
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_MEMBER_YEAR = 1710.0   # coupled graph, as written in the reference
+BYTES_PER_MEMBER_YEAR = 56.0    # 7 fp64 output series
+YEARS = 350
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--members", type=int, default=1 << 18, help="members per GPU (BASELINE config: 262144)")
+    ap.add_argument("--scenarios", type=int, default=8)
+    ap.add_argument("--e2e-outputs", default="Surface Temperature", help="comma list, or 'all'")
+    ap.add_argument("--cpu-sample-members", type=int, default=0, help="0 = auto-size to ~10 s")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_leg(args, M_sample, steps, warmup):
+    """The CPU restatement (oracle) timed with all host threads on a bounded sample of the same workload."""
+    from oracle import oracle as orc
+    from rscm_b200 import synthetic as syn
+    from tests.helpers import oracle_bindings, oracle_from_builder
+
+    b, binds, params, scen = syn.config3(M=M_sample, S=args.scenarios)
+    m = oracle_from_builder(b)
+    em = np.stack([s["Emissions|CO2|Anthropogenic"] for s in scen])
+    ob = oracle_bindings(b, binds)
+    out_names = syn.COUPLED_OUTPUTS
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        m.run_batch(ob, params, ["Emissions|CO2|Anthropogenic"], em, out_names)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    my = M_sample * args.scenarios * YEARS
+    return my / (sum(times) / len(times)), orc.max_threads(), sum(times) / len(times)
+
+
+def auto_cpu_sample(args, target_s=10.0):
+    v, cores, dt = cpu_leg(args, 256, 1, 0)
+    M = int(max(256, min(args.members, target_s * v / (args.scenarios * YEARS))))
+    return (M // 64) * 64
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    M = args.cpu_sample_members or auto_cpu_sample(args, target_s=8.0)
+    v, cores, dt = cpu_leg(args, M, args.steps, min(args.warmup, 1))
+    sample = f"{M} members x {args.scenarios} scenarios x {YEARS} years per step (bounded sample of {args.members} x {args.scenarios})"
+    line = {
+        "impl": "reference", "metric": "ensemble member-years/sec, coupled carbon+two-layer", "value": v, "unit": "member-years/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "coupled carbon cycle + CO2 ERF + two-layer, 262144 members x 8 scenarios x 350 yr (BASELINE configs[2])",
+                   "members_per_gpu": args.members, "scenarios": args.scenarios, "outputs": "all 7 series"},
+        "cpu_baseline": {"value": v, "unit": "member-years/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "member-years/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Rust (no toolchain here): this arm is the C oracle restating its arithmetic, OpenMP over members; it omits the "
+                "reference's per-step string/HashMap overhead and per-member model rebuild, so it is faster than the real reference",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from rscm_b200 import _ffi, synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    M, S = args.members, args.scenarios
+    b, binds, params, scen = syn.config3(M=M, S=S)
+    if world > 1:  # weak scaling: every rank gets its own member block of the same shape
+        params = syn.uniform_params(syn.COUPLED_RANGES, M, syn.SEED0 + 2 + 1000 * rank)
+    ens = b.build_ensemble(device=local).bind_parameters(binds)
+    ens.select_outputs(syn.COUPLED_OUTPUTS)
+    sc_host = ens.pack_scenarios(scen)
+    runs = S * M
+    d_params = torch.from_numpy(np.ascontiguousarray(params.T)).cuda()      # [cols][M] SoA
+    d_scen = torch.from_numpy(sc_host).cuda()
+    d_out = torch.empty((ens.output_rows, runs), dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        ens.run_device(d_params, d_scen, d_out, layout=0)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ens.kernel_ms(reset=True)
+    launches0 = ens.launch_count()
+    clocks = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    kernel_ms = ens.kernel_ms(reset=True)
+    launches = ens.launch_count() - launches0
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    my_per_step = world * runs * YEARS
+    value = my_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through rscm_b200_run_host --------------------------------------------
+    e2e_names = syn.COUPLED_OUTPUTS if args.e2e_outputs == "all" else [s.strip() for s in args.e2e_outputs.split(",")]
+    ens.select_outputs(e2e_names)
+    h_params = torch.from_numpy(np.ascontiguousarray(params)).pin_memory()   # [M][cols] = the reference's &[Vec<f64>]
+    h_scen = torch.from_numpy(sc_host).pin_memory()
+    h_out = torch.empty((ens.output_rows, runs), dtype=torch.float64).pin_memory()
+    hp, hs, ho = h_params.numpy(), h_scen.numpy(), h_out.numpy()
+    for _ in range(2):
+        ens.run(hp, hs, layout=1, out=ho)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ens.run(hp, hs, layout=1, out=ho)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = my_per_step * args.steps / float(t.item())
+    h2d = hp.nbytes + hs.nbytes
+    d2h = ho.nbytes
+    # sanity: the host path returns what the device path computed
+    ens.select_outputs(syn.COUPLED_OUTPUTS)
+
+    if rank == 0:
+        peak_tf = _ffi.C.c_double(0.0)
+        _ffi.check(_ffi.lib.rscm_b200_measure_fma_peak(local, 0, _ffi.C.byref(peak_tf)))
+        hbm_peak, hbm_src = measured_peaks()
+        per_launch_my = runs * YEARS
+        achieved_tf = FLOP_PER_MEMBER_YEAR * per_launch_my / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else None
+        achieved_gbs = BYTES_PER_MEMBER_YEAR * per_launch_my / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "ensemble member-years/sec, coupled carbon+two-layer", "value": value, "unit": "member-years/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "coupled carbon cycle + CO2 ERF + two-layer, 262144 members x 8 scenarios x 350 yr (BASELINE configs[2])",
+                "members_per_gpu": M, "scenarios": S, "years": YEARS, "outputs": "all 7 series, fp64, [rows][runs] in HBM",
+                "l2": "256 MB flush between timed steps; outputs per step (%.1f GB) also exceed L2" % (ens.output_rows * runs * 8 / 1e9),
+                "timing": "CUDA events around each step, summed; max over ranks",
+                "e2e_output_variables": e2e_names,
+            },
+            "e2e": {"value": e2e_value, "unit": "member-years/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "rscm_b200_run_host (ModelRunner.run_batch): pinned host params [M][cols] in, selected output series out"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
+                         "frac": (achieved_tf / peak_tf.value) if (achieved_tf and peak_tf.value) else None, "traffic": traffic,
+                         "kernel": "ensemble_kernel<double, coupled, write>", "kernel_ms": kernel_ms,
+                         "algorithmic": "1710 flop per member-year (SURVEY.md 8d) x %d member-years per launch" % per_launch_my,
+                         "peak_source": "DFMA micro-benchmark in this run (rscm_b200_measure_fma_peak); MEASURED_PEAKS.json has no FP64 entry"},
+            "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (achieved_gbs / hbm_peak) if achieved_gbs else None, "peak_source": hbm_src,
+                             "algorithmic": "56 B written per member-year"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            Ms = args.cpu_sample_members or auto_cpu_sample(args)
+            v, cores, dt = cpu_leg(args, Ms, 1, 0)
+            line["cpu_baseline"] = {"value": v, "unit": "member-years/s", "cores": cores, "kind": "port",
+                                    "sample": f"{Ms} members x {S} scenarios x {YEARS} yr, 1 pass ({dt:.1f} s), OpenMP static over members"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -125,7 +125,9 @@ typedef struct {
     int32_t n_times;                   /* T = time_axis.len() */
     const double *time_bounds;         /* T+1 (TimeAxis bounds, timeseries.rs:24-26) */
     int32_t compute_dtype;             /* 0 = fp64 (parity path), 1 = fp32 (1e-4 path) */
-    int32_t device;                    /* CUDA device ordinal, -1 = current */
+    int32_t device;                    /* CUDA device ordinal, -1 = current, -2 = host-only handle:
+                                          graph compile + introspection only, every run call
+                                          returns RSCM_B200_ENODEVICE (used by CPU-side tests) */
 } rscm_b200_graph_desc;
 
 typedef struct rscm_b200_ensemble rscm_b200_ensemble;

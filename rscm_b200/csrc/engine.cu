@@ -313,6 +313,19 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
         return fail(nullptr, RSCM_B200_EUNSUPPORTED,
                     "no device program for this component graph (ahead-of-time registry miss); there is no CPU fallback");
     }
+    h->Tpad = (g.T + 3) & ~3;
+    h->slot_col.assign(g.n_slots, -1);
+    h->init_col.assign(g.n_cells, -1);
+    for (size_t v = 0; v < g.vars.size(); ++v) h->sel_vars.push_back(static_cast<int>(v));
+    h->t_start = 0;
+    h->t_stop = g.T;
+    h->t_step = 1;
+    recompute_selection(h);
+    if (desc->device == -2) { // host-only handle: graph compile + introspection, never runs
+        h->device = -2;
+        *out = h;
+        return RSCM_B200_OK;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -326,14 +339,6 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
         }
     }
     cudaGetDevice(&h->device);
-    h->Tpad = (g.T + 3) & ~3;
-    h->slot_col.assign(g.n_slots, -1);
-    h->init_col.assign(g.n_cells, -1);
-    for (size_t v = 0; v < g.vars.size(); ++v) h->sel_vars.push_back(static_cast<int>(v));
-    h->t_start = 0;
-    h->t_stop = g.T;
-    h->t_step = 1;
-    recompute_selection(h);
 
     // RK4 sub-step tables
     if (g.n_rk > 0) {
@@ -497,6 +502,7 @@ int rscm_b200_set_target(rscm_b200_ensemble *h, const rscm_b200_obs *obs, int64_
     h->n_obs_rows = static_cast<int>(row_var.size());
     for (int r = 0; r < h->n_obs_rows; ++r) h->obs_cell[r] = g.vars[row_var[r]].cell0;
     h->normalize = normalize ? 1 : 0;
+    if (h->device < 0) { h->has_target = true; return RSCM_B200_OK; }
     if (h->d_obs) cudaFree(h->d_obs);
     h->d_obs = nullptr;
     if (h->n_obs_rows > 0) {
@@ -518,6 +524,7 @@ int rscm_b200_set_priors(rscm_b200_ensemble *h, const rscm_b200_prior *priors, i
     h->n_priors = 0;
     if (n_columns <= 0) return RSCM_B200_OK;
     if (n_columns != h->n_cols) return fail(h, RSCM_B200_EINVAL, "one prior per bound parameter column required");
+    if (h->device < 0) { h->n_priors = n_columns; return RSCM_B200_OK; }
     std::vector<rscm_dev::PriorDev> p(n_columns);
     for (int i = 0; i < n_columns; ++i) {
         p[i].kind = priors[i].kind; p[i].pad = 0;
@@ -533,6 +540,7 @@ int rscm_b200_run_device(rscm_b200_ensemble *h, const double *params, int64_t M,
                          const double *scenarios, int64_t S, double *out, uint8_t *status, void *stream)
 {
     if (!h || !out) return fail(h, RSCM_B200_EINVAL, "null argument");
+    if (h->device < 0) return fail(h, RSCM_B200_ENODEVICE, "host-only handle (device = -2) cannot run; there is no CPU fallback");
     CU(cudaSetDevice(h->device));
     return enqueue(h, params, M, params_layout, scenarios, S, out, status, nullptr, nullptr, true, false,
                    static_cast<cudaStream_t>(stream), true);
@@ -543,6 +551,7 @@ int rscm_b200_logpost_device(rscm_b200_ensemble *h, const double *params, int64_
                              rscm_b200_logpost_summary *summary, void *stream)
 {
     if (!h || !logpost) return fail(h, RSCM_B200_EINVAL, "null argument");
+    if (h->device < 0) return fail(h, RSCM_B200_ENODEVICE, "host-only handle (device = -2) cannot run; there is no CPU fallback");
     CU(cudaSetDevice(h->device));
     static_assert(sizeof(rscm_b200_logpost_summary) == sizeof(rscm_dev::SummaryDev), "summary layout");
     return enqueue(h, params, M, params_layout, scenarios, S, nullptr, nullptr, logpost,
@@ -553,6 +562,7 @@ int rscm_b200_run_host(rscm_b200_ensemble *h, const double *params, int64_t M, i
                        const double *scenarios, int64_t S, double *out, uint8_t *status)
 {
     if (!h || !out) return fail(h, RSCM_B200_EINVAL, "null argument");
+    if (h->device < 0) return fail(h, RSCM_B200_ENODEVICE, "host-only handle (device = -2) cannot run; there is no CPU fallback");
     CU(cudaSetDevice(h->device));
     const rscm::Graph &g = h->g;
     if (M <= 0) return fail(h, RSCM_B200_EINVAL, "M must be positive");
@@ -629,6 +639,7 @@ int rscm_b200_logpost_host(rscm_b200_ensemble *h, const double *params, int64_t 
                            const double *scenarios, int64_t S, double *logpost, rscm_b200_logpost_summary *summary)
 {
     if (!h || !logpost) return fail(h, RSCM_B200_EINVAL, "null argument");
+    if (h->device < 0) return fail(h, RSCM_B200_ENODEVICE, "host-only handle (device = -2) cannot run; there is no CPU fallback");
     CU(cudaSetDevice(h->device));
     const rscm::Graph &g = h->g;
     if (M <= 0) return fail(h, RSCM_B200_EINVAL, "M must be positive");

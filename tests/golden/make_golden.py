@@ -1,0 +1,56 @@
+"""Extracts the golden vectors the reference's own regression tests hold for the hot path
+into small fixtures that travel to the GPU box (/root/reference does not exist there).
+
+Source: /root/reference/tests/regression/data/ghg_forcing/{01_concentration_driven,
+02_ghg_forcing_olbl}.csv (+ *_config.json) — MAGICC7 (Fortran) concentrations -> ERF|CO2/CH4/N2O,
+compared by tests/regression/test_ghg_forcing.py:237-331 at rtol 1e-5 / atol 1e-6 with
+PI = first-year concentrations and actual[1:] vs expected[:-1].
+
+Run once in the build container:  python tests/golden/make_golden.py
+"""
+import csv
+import json
+import os
+
+import numpy as np
+
+REF = "/root/reference/tests/regression/data/ghg_forcing"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+VARS = {
+    "co2": "Atmospheric Concentrations|CO2",
+    "ch4": "Atmospheric Concentrations|CH4",
+    "n2o": "Atmospheric Concentrations|N2O",
+    "erf_co2": "Effective Radiative Forcing|CO2",
+    "erf_ch4": "Effective Radiative Forcing|CH4",
+    "erf_n2o": "Effective Radiative Forcing|N2O",
+}
+
+
+def load(name):
+    with open(os.path.join(REF, name + ".csv")) as f:
+        rows = list(csv.reader(f))
+    header = rows[0]
+    ivar = header.index("variable")
+    ireg = header.index("region")
+    tcols = [i for i, h in enumerate(header) if h[:4].isdigit()]
+    years = np.array([float(header[i][:4]) for i in tcols])
+    out = {"years": years}
+    for key, var in VARS.items():
+        for r in rows[1:]:
+            if r[ivar] == var and r[ireg] == "World":
+                out[key] = np.array([float(r[i]) for i in tcols])
+                break
+        else:
+            raise KeyError(var)
+    with open(os.path.join(REF, name + "_config.json")) as f:
+        cfg = json.load(f)
+    return out, cfg
+
+
+if __name__ == "__main__":
+    for name in ("01_concentration_driven", "02_ghg_forcing_olbl"):
+        data, cfg = load(name)
+        keep = {k: cfg[k] for k in cfg if k.startswith("core_")}
+        np.savez_compressed(os.path.join(HERE, f"ghg_forcing_{name[:2]}.npz"), config=json.dumps(keep), **data)
+        print(name, {k: v.shape for k, v in data.items()}, keep)
