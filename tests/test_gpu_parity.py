@@ -63,7 +63,7 @@ def test_config1_single_two_layer_run_model_api():
     for n in ("Surface Temperature", "Deep Ocean Temperature", "Effective Radiative Forcing"):
         assert rel_err(res.get_timeseries_by_name(n).values(), ref[n]) <= TOL64
     ts = res.get_timeseries_by_name("Surface Temperature").values()
-    assert ts[0] == 0.0 and 1.5 < ts[-1] < 4.0
+    assert ts[0] == 0.0 and 1.5 < ts[-1] < 6.0
 
 
 def test_model_step_reveals_one_index_at_a_time():
