@@ -251,7 +251,7 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp))["dram_bytes_per_member_year"] * per_launch_my
             except Exception:
                 traffic = None
         line = {
