@@ -37,7 +37,7 @@ template <> __device__ __forceinline__ float r_nan<float>() { return __int_as_fl
 // ---------------------------------------------------------------------------
 // TwoLayer — crates/rscm-two-layer/src/component.rs
 //   P: lambda0, a, efficacy, eta, heat_capacity_surface, heat_capacity_deep
-//   D: efficacy*eta, 1/Cs, eta/Cd
+//   D: k1, k2, k3 (below), 1/Cs, eta/Cd
 //   in : erf (get()), Ts (at_start), Td (at_start)      out: Ts, Td
 // RK4 (ode_solvers 0.6.1 as called from rscm-core/src/ivp/mod.rs:245-253):
 // nsub fixed steps of h = 0.1 (component.rs:240); the third state (cumulative
@@ -45,43 +45,48 @@ template <> __device__ __forceinline__ float r_nan<float>() { return __int_as_fl
 // reference, so it is not computed here.
 // ---------------------------------------------------------------------------
 constexpr int TWO_LAYER_NP = 6;
-constexpr int TWO_LAYER_ND = 3;
+constexpr int TWO_LAYER_ND = 5;
 
+// With x = efficacy*eta (same association as component.rs:176) the surface equation
+//   dTs = (F - (lambda0 - a Ts) Ts - x (Ts - Td)) / Cs
+// is evaluated in the expanded form  F/Cs + Ts (k1 + k3 Ts) + k2 Td  with
+//   k1 = -(lambda0 + x)/Cs, k2 = x/Cs, k3 = a/Cs      (3 FMAs per evaluation)
+// and dTd = (Ts - Td) * (eta/Cd).  Same polynomial, different association: O(1 ulp).
 template <class R>
 __device__ __forceinline__ void two_layer_prepare(const R *P, R *D)
 {
-    D[0] = P[2] * P[3];    // efficacy * eta (same association as component.rs:176)
-    D[1] = R(1) / P[4];    // reciprocal of heat_capacity_surface
-    D[2] = P[3] / P[5];    // eta / heat_capacity_deep
+    const R x = P[2] * P[3];
+    const R inv_cs = R(1) / P[4];
+    D[0] = -(P[0] + x) * inv_cs;
+    D[1] = x * inv_cs;
+    D[2] = P[1] * inv_cs;
+    D[3] = inv_cs;
+    D[4] = P[3] / P[5];
 }
 
 template <class R>
-__device__ __forceinline__ void two_layer_rhs(R lam0, R a, R eff_eta, R inv_cs, R eta_cd, R erf,
-                                              R ts, R td, R &dts, R &dtd)
+__device__ __forceinline__ void two_layer_rhs(R k0, R k1, R k2, R k3, R eta_cd, R ts, R td, R &dts, R &dtd)
 {
     // calculate_dy_dt — component.rs:160-188
-    const R diff = ts - td;
-    const R lambda_eff = lam0 - a * ts;
-    dts = (erf - lambda_eff * ts - eff_eta * diff) * inv_cs;
-    dtd = diff * eta_cd;
+    dts = ts * (k3 * ts + k1) + (td * k2 + k0);
+    dtd = (ts - td) * eta_cd;
 }
 
 template <class R>
-__device__ __forceinline__ bool two_layer_solve(const R *P, const R *D, const R *in, R *out, int nsub)
+__device__ __forceinline__ bool two_layer_solve(const R *, const R *D, const R *in, R *out, int nsub)
 {
     if (nsub < 0) return false; // get_last_step assertion (ivp/mod.rs:94-97) would fire
-    const R lam0 = P[0], a = P[1];
-    const R eff_eta = D[0], inv_cs = D[1], eta_cd = D[2];
-    const R erf = in[0];
+    const R k1 = D[0], k2 = D[1], k3 = D[2], eta_cd = D[4];
+    const R k0 = in[0] * D[3]; // F / Cs, F frozen over the step
     R ts = in[1], td = in[2];
     const R h = R(0.1), hh = R(0.1) / R(2), h6 = R(0.1) / R(6);
 #pragma unroll 2
     for (int s = 0; s < nsub; ++s) {
         R a0, b0, a1, b1, a2, b2, a3, b3;
-        two_layer_rhs(lam0, a, eff_eta, inv_cs, eta_cd, erf, ts, td, a0, b0);
-        two_layer_rhs(lam0, a, eff_eta, inv_cs, eta_cd, erf, ts + a0 * hh, td + b0 * hh, a1, b1);
-        two_layer_rhs(lam0, a, eff_eta, inv_cs, eta_cd, erf, ts + a1 * hh, td + b1 * hh, a2, b2);
-        two_layer_rhs(lam0, a, eff_eta, inv_cs, eta_cd, erf, ts + a2 * h, td + b2 * h, a3, b3);
+        two_layer_rhs(k0, k1, k2, k3, eta_cd, ts, td, a0, b0);
+        two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a0 * hh, td + b0 * hh, a1, b1);
+        two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a1 * hh, td + b1 * hh, a2, b2);
+        two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a2 * h, td + b2 * h, a3, b3);
         ts = ts + (a0 + a1 * R(2) + a2 * R(2) + a3) * h6;
         td = td + (b0 + b1 * R(2) + b2 * R(2) + b3) * h6;
     }
@@ -93,7 +98,7 @@ __device__ __forceinline__ bool two_layer_solve(const R *P, const R *D, const R 
 // ---------------------------------------------------------------------------
 // CarbonCycle — crates/rscm-components/src/components/carbon_cycle.rs
 //   P: tau, conc_pi, alpha_temperature, step_size
-//   D: 1/tau
+//   D: 1/tau, step_size/6
 //   in : emissions (get), temperature (get), concentration, cumulative_emissions,
 //        cumulative_uptake (at_start)      out: same three states
 // Hoisted per annual step (inputs are frozen over the step, :144-145):
@@ -101,12 +106,13 @@ __device__ __forceinline__ bool two_layer_solve(const R *P, const R *D, const R 
 // dy[2] = E is constant over the step, so its RK4 increment is one value.
 // ---------------------------------------------------------------------------
 constexpr int CARBON_CYCLE_NP = 4;
-constexpr int CARBON_CYCLE_ND = 1;
+constexpr int CARBON_CYCLE_ND = 2;
 
 template <class R>
 __device__ __forceinline__ void carbon_cycle_prepare(const R *P, R *D)
 {
     D[0] = R(1) / P[0];
+    D[1] = P[3] / R(6); // h/6
 }
 
 template <class R>
@@ -118,8 +124,8 @@ __device__ __forceinline__ bool carbon_cycle_solve(const R *P, const R *D, const
     const R emissions = in[0], temperature = in[1];
     R conc = in[2], cum_e = in[3], cum_u = in[4];
     const R inv_life = r_exp<R>(-(alpha * temperature)) * D[0];
-    const R e_ppm = emissions / gtc;
-    const R hh = h / R(2), h6 = h / R(6);
+    const R e_ppm = emissions * (R(1) / gtc); // reciprocal of the constant: 1 ulp from E/GTC_PER_PPM
+    const R hh = h * R(0.5), h6 = D[1];
     const R e_inc = (emissions + emissions * R(2) + emissions * R(2) + emissions) * h6;
     // The concentration is integrated as the anomaly x = C - C_pi (exact subtraction for
     // C within a factor 2 of C_pi), so uptake u = x/lifetime is one multiply and is
@@ -149,21 +155,22 @@ __device__ __forceinline__ bool carbon_cycle_solve(const R *P, const R *D, const
 
 // ---------------------------------------------------------------------------
 // CO2ERF — crates/rscm-components/src/components/co2_erf.rs:57-60
-//   P: erf_2xco2, conc_pi      D: erf_2xco2 / ln 2
+//   P: erf_2xco2, conc_pi      D: erf_2xco2 / ln 2, 1/conc_pi
 // ---------------------------------------------------------------------------
 constexpr int CO2_ERF_NP = 2;
-constexpr int CO2_ERF_ND = 1;
+constexpr int CO2_ERF_ND = 2;
 
 template <class R>
 __device__ __forceinline__ void co2_erf_prepare(const R *P, R *D)
 {
     D[0] = P[0] / R(0.6931471805599453094172321);
+    D[1] = R(1) / P[1];
 }
 
 template <class R>
 __device__ __forceinline__ bool co2_erf_solve(const R *P, const R *D, const R *in, R *out, int)
 {
-    out[0] = D[0] * r_log<R>(R(1) + (in[0] - P[1]) / P[1]);
+    out[0] = D[0] * r_log<R>(R(1) + (in[0] - P[1]) * D[1]);
     return true;
 }
 

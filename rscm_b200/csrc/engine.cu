@@ -221,8 +221,7 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
         a.init_col[c] = h->init_col[c];
         const rscm::Variable &var = g.vars[g.cell_var[c]];
         a.init_def[c] = var.has_initial ? var.initial : std::numeric_limits<double>::quiet_NaN();
-        a.out_base[c] = write ? h->out_base[c] : -1;
-        a.out_tmul[c] = h->out_tmul[c];
+        a.out_off[c] = (write && h->out_base[c] >= 0) ? static_cast<long long>(h->out_base[c]) * a.runs * 8 : -1;
     }
     const dim3 grid(static_cast<unsigned>((M + rscm_dev::BLOCK - 1) / rscm_dev::BLOCK), static_cast<unsigned>(S));
     if (logp && d_summary) {

@@ -24,7 +24,7 @@ static const std::vector<KindInfo> &kinds()
           {"Surface Temperature", REQ_STATE, RSCM_B200_SCALAR},
           {"Deep Ocean Temperature", REQ_STATE, RSCM_B200_SCALAR}},
          {"lambda0", "a", "efficacy", "eta", "heat_capacity_surface", "heat_capacity_deep"},
-         3, -1, {1, 1, 1, 1, 1, 1}},
+         5, -1, {1, 1, 1, 1, 1, 1}, 10},
         {RSCM_B200_CARBON_CYCLE, "CarbonCycle", "carbon_cycle",
          // crates/rscm-components/src/components/carbon_cycle.rs:62-72
          {{"Emissions|CO2|Anthropogenic", REQ_INPUT, RSCM_B200_SCALAR},
@@ -33,13 +33,13 @@ static const std::vector<KindInfo> &kinds()
           {"Cumulative Emissions|CO2", REQ_STATE, RSCM_B200_SCALAR},
           {"Cumulative Land Uptake", REQ_STATE, RSCM_B200_SCALAR}},
          {"tau", "conc_pi", "alpha_temperature", "step_size"},
-         1, 3, {1, 1, 1, 0}},
+         2, 3, {1, 1, 1, 0}, 10},
         {RSCM_B200_CO2_ERF, "CO2ERF", "co2_erf",
          // crates/rscm-components/src/components/co2_erf.rs:36-44
          {{"Atmospheric Concentration|CO2", REQ_INPUT, RSCM_B200_SCALAR},
           {"Effective Radiative Forcing|CO2", REQ_OUTPUT, RSCM_B200_SCALAR}},
          {"erf_2xco2", "conc_pi"},
-         1, -2, {1, 1}},
+         2, -2, {1, 1}, 4},
         {RSCM_B200_GHG_FORCING, "GhgForcing", "ghg_forcing",
          // crates/rscm-magicc/src/forcing/ghg.rs (derive block at top of file)
          {{"Atmospheric Concentration|CO2", REQ_INPUT, RSCM_B200_SCALAR},
@@ -52,7 +52,7 @@ static const std::vector<KindInfo> &kinds()
           "olbl_co2_a1", "olbl_co2_b1", "olbl_co2_c1", "olbl_co2_d1", "olbl_ch4_a3", "olbl_ch4_b3",
           "olbl_ch4_d3", "olbl_n2o_a2", "olbl_n2o_b2", "olbl_n2o_c2", "olbl_n2o_d2", "adjust_co2",
           "adjust_ch4", "adjust_n2o"},
-         1, -2, {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}},
+         1, -2, {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 40},
     };
     return k;
 }
@@ -160,6 +160,11 @@ static void emit_program(Graph &g)
     o << "    static constexpr int NC = " << g.n_cells << ";\n";
     o << "    static constexpr int NP = " << g.n_slots << ";\n";
     o << "    static constexpr int ND = " << g.n_derived << ";\n";
+    int weight = 0;
+    for (const Node &n : g.nodes)
+        if (n.kind != KIND_AGGREGATOR) weight += kind_info(n.kind)->reg_weight;
+    // 8 CTAs of 128 threads per SM = 64 registers per thread; register-hungry programs get 4 (128 registers)
+    o << "    static constexpr int MIN_BLOCKS = " << (weight <= 32 ? 8 : 4) << ";\n";
     o << "    __host__ __device__ static constexpr int exo_row(int c) { return ";
     for (int c = 0; c < g.n_cells; ++c) {
         const Variable &v = g.vars[g.cell_var[c]];
@@ -170,6 +175,12 @@ static void emit_program(Graph &g)
     for (int c = 0; c < g.n_cells; ++c)
         if (g.vars[g.cell_var[c]].endogenous) o << "c == " << c << " || ";
     o << "false; }\n";
+    o << "    __host__ __device__ static constexpr int regions(int c) { return ";
+    for (int c = 0; c < g.n_cells; ++c) {
+        const int r = g.vars[g.cell_var[c]].n_regions;
+        if (r != 1) o << "c == " << c << " ? " << r << " : ";
+    }
+    o << "1; }\n";
     o << "    template <class R> __device__ __forceinline__ static void prepare(const R *P, R *D) {\n";
     o << "        (void)P; (void)D;\n";
     for (size_t ni = 0; ni < g.nodes.size(); ++ni) {

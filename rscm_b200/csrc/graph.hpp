@@ -34,6 +34,7 @@ struct KindInfo {
     int n_derived;
     int rk_step_param; // index of the RK4 step-size parameter, -1: fixed 0.1, -2: no RK4
     std::vector<int> bindable; // 1 if the parameter may be bound to a member column
+    int reg_weight;            // rough register appetite; decides the kernel's min-CTAs-per-SM hint
 };
 
 const KindInfo *kind_info(int kind);

@@ -76,8 +76,7 @@ struct KArgs {
     double slot_def[MAX_SLOTS];
     int init_col[MAX_CELLS];
     double init_def[MAX_CELLS];
-    int out_base[MAX_CELLS]; // first output row of this cell (var row0 + region) or -1
-    int out_tmul[MAX_CELLS]; // regions of the cell's variable
+    long long out_off[MAX_CELLS]; // byte offset of the cell's first output row (row * runs * 8) or -1
 };
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) -----------------------------
@@ -178,7 +177,7 @@ __device__ __forceinline__ void obs_accumulate(const KArgs &a, const double *s_o
 }
 
 template <class R, class Prog, bool WRITE, bool LOGP>
-__global__ void __launch_bounds__(BLOCK) ensemble_kernel(const __grid_constant__ KArgs a)
+__global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::MIN_BLOCKS - 1 : Prog::MIN_BLOCKS) ensemble_kernel(const __grid_constant__ KArgs a)
 {
     constexpr int NC = Prog::NC;
     constexpr int NP = Prog::NP;
@@ -243,18 +242,22 @@ __global__ void __launch_bounds__(BLOCK) ensemble_kernel(const __grid_constant__
     unsigned fail = 0;
 
     // index 0: initial values / exogenous echo (model/builder.rs:771-781)
-    int tsel = 0; // next selected-time ordinal
+    // Output addressing: rows of a variable with R regions advance by R*runs per selected time,
+    // so one running byte pointer per region class (1, 2, 4) plus a host-precomputed per-cell
+    // byte offset (constant bank) gives each store two integer adds.
     int tnext = a.t_start;
+    const long long row_bytes = a.runs * 8;
+    char *p1 = reinterpret_cast<char *>(a.out) + run * 8, *p2 = p1, *p4 = p1;
     if (WRITE) {
         if (tnext == 0 && tnext < a.t_stop) {
             if (active) {
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
-                    if (a.out_base[c] >= 0)
-                        store_stream(a.out + static_cast<long long>(a.out_base[c]) * a.runs + run,
+                    if (a.out_off[c] >= 0)
+                        store_stream(reinterpret_cast<double *>((Prog::regions(c) == 1 ? p1 : Prog::regions(c) == 2 ? p2 : p4) + a.out_off[c]),
                                      static_cast<double>(cur[c]));
             }
-            tsel = 1;
+            p1 += row_bytes; p2 += 2 * row_bytes; p4 += 4 * row_bytes;
             tnext += a.t_step;
         }
     }
@@ -274,12 +277,11 @@ __global__ void __launch_bounds__(BLOCK) ensemble_kernel(const __grid_constant__
                 if (active) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
-                        if (a.out_base[c] >= 0)
-                            store_stream(a.out + (static_cast<long long>(a.out_base[c]) +
-                                                  static_cast<long long>(tsel) * a.out_tmul[c]) * a.runs + run,
+                        if (a.out_off[c] >= 0)
+                            store_stream(reinterpret_cast<double *>((Prog::regions(c) == 1 ? p1 : Prog::regions(c) == 2 ? p2 : p4) + a.out_off[c]),
                                          static_cast<double>(nxt[c]));
                 }
-                ++tsel;
+                p1 += row_bytes; p2 += 2 * row_bytes; p4 += 4 * row_bytes;
                 tnext += a.t_step;
             }
         }
