@@ -153,7 +153,7 @@ def run_reference(args):
         "note": "reference is Rust (no toolchain here): this arm is the C oracle restating its arithmetic, OpenMP over members; it omits the "
                 "reference's per-step string/HashMap overhead and per-member model rebuild, so it is faster than the real reference",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -283,12 +283,23 @@ def run_ours(args):
             v, cores, dt = cpu_leg(args, Ms, 1, 0)
             line["cpu_baseline"] = {"value": v, "unit": "member-years/s", "cores": cores, "kind": "port",
                                     "sample": f"{Ms} members x {S} scenarios x {YEARS} yr, 1 pass ({dt:.1f} s), OpenMP static over members"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line: dict) -> None:
+    """The JSON line goes to the process's real stdout; everything else that writes to fd 1
+    (e.g. NCCL's version banner) was redirected to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
