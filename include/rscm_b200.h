@@ -158,6 +158,8 @@ int rscm_b200_execution_order(const rscm_b200_ensemble *h, int *order, int capac
 int rscm_b200_variable_source(const rscm_b200_ensemble *h, int component, const char *variable);
 /* canonical text of the fused device program chosen for this graph */
 const char *rscm_b200_program_signature(const rscm_b200_ensemble *h);
+/* 0: the program comes from the ahead-of-time registry; 1: compiled at run time (NVRTC, sm_100a) */
+int rscm_b200_program_is_jit(const rscm_b200_ensemble *h);
 /* index of the time point whose "{:.6}" key equals that of `time`
  * (crates/rscm-calibrate/src/likelihood.rs:40-42); -1 if none */
 int rscm_b200_time_index(const rscm_b200_ensemble *h, double time);

@@ -127,6 +127,7 @@ SYMBOLS = {
     "rscm_b200_execution_order": (C.c_int, [_H, C.POINTER(C.c_int), C.c_int]),
     "rscm_b200_variable_source": (C.c_int, [_H, C.c_int, C.c_char_p]),
     "rscm_b200_program_signature": (C.c_char_p, [_H]),
+    "rscm_b200_program_is_jit": (C.c_int, [_H]),
     "rscm_b200_time_index": (C.c_int, [_H, C.c_double]),
     "rscm_b200_bind_parameters": (C.c_int, [_H, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_int]),
     "rscm_b200_select_outputs": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32]),

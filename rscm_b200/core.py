@@ -597,6 +597,9 @@ class Ensemble:
     def program_signature(self) -> str:
         return _ffi.lib.rscm_b200_program_signature(self._h).decode()
 
+    def program_is_jit(self) -> bool:
+        return bool(_ffi.lib.rscm_b200_program_is_jit(self._h))
+
     def time_index(self, time: float) -> int:
         return _ffi.lib.rscm_b200_time_index(self._h, float(time))
 

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "graph.hpp"
+#include "jit.hpp"
 #include "kernel.cuh"
 
 using rscm_dev::KArgs;
@@ -59,6 +60,10 @@ struct rscm_b200_ensemble {
     int dtype = 0;
     int device = 0;
     const AotEntry *prog = nullptr;
+    bool use_jit = false; // program compiled at run time (jit.cpp) instead of taken from the AOT registry
+    std::string jit_cubin;
+    std::vector<std::string> jit_names;
+    rscm::JitProgram jit;
     std::string err;
     int Tpad = 0;
 
@@ -254,8 +259,14 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     }
     h->ev_next = (ei + 1) % 64;
     CU(cudaEventRecord(h->events[ei].first, st));
-    cudaError_t e = h->prog->launch(h->dtype, write, logp, grid, smem_bytes(h, logp), st, a);
-    if (e != cudaSuccess) return fail(h, RSCM_B200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    if (h->use_jit) {
+        const int variant = (write && !logp) ? 0 : ((!write && logp) ? 1 : 2);
+        const int rc = rscm::jit_launch(h->jit, variant, grid.x, grid.y, rscm_dev::BLOCK, static_cast<unsigned>(smem_bytes(h, logp)), st, &a);
+        if (rc != 0) return fail(h, RSCM_B200_ECUDA, "cuLaunchKernel failed with CUresult " + std::to_string(rc));
+    } else {
+        cudaError_t e = h->prog->launch(h->dtype, write, logp, grid, smem_bytes(h, logp), st, a);
+        if (e != cudaSuccess) return fail(h, RSCM_B200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    }
     CU(cudaEventRecord(h->events[ei].second, st));
     h->ev_pending[ei] = 1;
     h->launches++;
@@ -308,9 +319,15 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
     for (const AotEntry &e : g_aot)
         if (g.signature == e.signature) { h->prog = &e; break; }
     if (!h->prog) {
-        delete h;
-        return fail(nullptr, RSCM_B200_EUNSUPPORTED,
-                    "no device program for this component graph (ahead-of-time registry miss); there is no CPU fallback");
+        // not one of the ahead-of-time graphs: compile the emitted program at run time (NVRTC)
+        std::string jerr;
+        if (!rscm::jit_compile_cubin(g.program_source, h->dtype, h->jit_cubin, h->jit_names, jerr)) {
+            delete h;
+            return fail(nullptr, RSCM_B200_EUNSUPPORTED,
+                        "no ahead-of-time device program for this component graph and run-time compilation failed "
+                        "(there is no CPU fallback): " + jerr);
+        }
+        h->use_jit = true;
     }
     h->Tpad = (g.T + 3) & ~3;
     h->slot_col.assign(g.n_slots, -1);
@@ -338,6 +355,14 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
         }
     }
     cudaGetDevice(&h->device);
+    if (h->use_jit) {
+        cudaFree(nullptr); // make the primary context current for the driver-API module load
+        std::string jerr;
+        if (!rscm::jit_load(h->jit_cubin, h->jit_names, h->jit, jerr)) {
+            delete h;
+            return fail(nullptr, RSCM_B200_ECUDA, "loading the run-time compiled program failed: " + jerr);
+        }
+    }
 
     // RK4 sub-step tables
     if (g.n_rk > 0) {
@@ -423,6 +448,7 @@ int rscm_b200_variable_source(const rscm_b200_ensemble *h, int component, const 
     return -1;
 }
 const char *rscm_b200_program_signature(const rscm_b200_ensemble *h) { return h->g.signature.c_str(); }
+int rscm_b200_program_is_jit(const rscm_b200_ensemble *h) { return h->use_jit ? 1 : 0; }
 int rscm_b200_time_index(const rscm_b200_ensemble *h, double time) { return rscm::time_index_for(h->g, time); }
 
 int rscm_b200_bind_parameters(rscm_b200_ensemble *h, int n_bindings, const char *const *slots, const int32_t *columns,

@@ -232,6 +232,33 @@ def test_ghg_forcing_into_two_layer_with_sum_aggregate():
     gpu_vs_oracle(b, binds, p, scen)
 
 
+def test_run_time_compiled_graph_parity(tmp_path, monkeypatch):
+    """A graph outside the AOT registry (CO2ERF on exogenous concentrations -> Sum aggregate -> TwoLayer):
+    emitted, compiled by NVRTC for sm_100a, loaded through the driver API, and checked like the others."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    from rscm_b200.two_layer import TwoLayerBuilder
+    axis = syn.time_axis()
+    schema = VariableSchema()
+    schema.add_variable("Atmospheric Concentration|CO2", "ppm")
+    schema.add_variable("Effective Radiative Forcing|CO2", "W/m^2")
+    schema.add_variable("Effective Radiative Forcing|Other", "W/m^2")
+    schema.add_aggregate("Effective Radiative Forcing", "W/m^2", "Weighted", ["Effective Radiative Forcing|CO2", "Effective Radiative Forcing|Other"],
+                         weights=[1.0, 0.5])
+    b = (ModelBuilder().with_time_axis(axis).with_schema(schema)
+         .with_rust_component(CO2ERFBuilder.from_parameters({"erf_2xco2": 3.7, "conc_pi": 278.0}).build())
+         .with_rust_component(TwoLayerBuilder.from_parameters(syn.TWO_LAYER_DEFAULTS).build())
+         .with_initial_values({"Surface Temperature": 0.0, "Deep Ocean Temperature": 0.0}))
+    years = axis.values()
+    conc = 278.0 * np.exp(0.004 * np.maximum(0.0, years - 1850.0))
+    other = np.where(years > 1990, -0.3, np.nan)  # exogenous contributor with NaNs: dropped by the aggregate while NaN
+    scen = [{"Atmospheric Concentration|CO2": conc * f, "Effective Radiative Forcing|Other": other} for f in (1.0, 1.05)]
+    binds = {**syn.TWO_LAYER_BINDINGS, "erf_2xco2": "CO2ERF.erf_2xco2"}
+    p = np.column_stack([syn.uniform_params(syn.TWO_LAYER_RANGES, 200, 9), np.random.default_rng(4).uniform(3.4, 4.0, 200)])
+    got, ref, _, ens = gpu_vs_oracle(b, binds, p, scen)
+    assert ens.program_is_jit()
+    assert not np.isnan(got["Effective Radiative Forcing"][1:]).any()
+
+
 # ---- failure semantics -------------------------------------------------------------------------------------------
 def test_rk4_assertion_failure_is_data_not_an_error():
     axis = TimeAxis.from_bounds(np.array([2000.0, 2001.0, 2002.05, 2003.05, 2004.05]))

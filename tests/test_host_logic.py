@@ -63,16 +63,20 @@ def test_unknown_component_kind_is_rejected_not_emulated():
         host_only(b)
 
 
-def test_graph_without_device_program_is_unsupported():
-    # a graph shape outside the ahead-of-time registry: two CO2ERF components fed by the same concentration
+def test_graph_outside_the_aot_registry_is_compiled_at_run_time(tmp_path, monkeypatch):
+    """A graph shape that is not one of the ahead-of-time programs goes through the emitter + NVRTC
+    (sm_100a cubin, no GPU needed to compile); the named graphs do not."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
     b = (ModelBuilder().with_time_axis(syn.time_axis())
          .with_rust_component(CO2ERFBuilder.from_parameters({"erf_2xco2": 3.7, "conc_pi": 278.0}).build())
          .with_rust_component(TwoLayerBuilder.from_parameters(syn.TWO_LAYER_DEFAULTS).build())
          .with_rust_component(GhgForcingBuilder.from_parameters({}).build())
          .with_initial_values({"Surface Temperature": 0.0, "Deep Ocean Temperature": 0.0}))
-    with pytest.raises(_ffi.EngineError) as e:
-        host_only(b)
-    assert e.value.code == _ffi.EUNSUPPORTED
+    ens = host_only(b)
+    assert ens.program_is_jit()
+    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))  # disk cache written
+    assert host_only(b).program_is_jit()                            # second build served from the cache
+    assert not host_only(syn.coupled_builder()).program_is_jit()
 
 
 # ---- graph compiler == ModelBuilder::build (checked against the independent oracle implementation) ---------
