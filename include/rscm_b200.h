@@ -50,7 +50,11 @@ typedef enum {
     RSCM_B200_TWO_LAYER = 1,    /* crates/rscm-two-layer/src/component.rs:38-90 */
     RSCM_B200_CARBON_CYCLE = 2, /* crates/rscm-components/src/components/carbon_cycle.rs:24-40 */
     RSCM_B200_CO2_ERF = 3,      /* crates/rscm-components/src/components/co2_erf.rs:18-25 */
-    RSCM_B200_GHG_FORCING = 5   /* crates/rscm-magicc/src/parameters/ghg_forcing.rs */
+    RSCM_B200_GHG_FORCING = 5,  /* crates/rscm-magicc/src/parameters/ghg_forcing.rs */
+    RSCM_B200_OZONE_FORCING = 6,    /* crates/rscm-magicc/src/parameters/ozone_forcing.rs */
+    RSCM_B200_AEROSOL_DIRECT = 7,   /* crates/rscm-magicc/src/parameters/aerosol.rs (AerosolDirectParameters) */
+    RSCM_B200_AEROSOL_INDIRECT = 8, /* crates/rscm-magicc/src/parameters/aerosol.rs (AerosolIndirectParameters) */
+    RSCM_B200_CLIMATE_UDEB = 9      /* crates/rscm-magicc/src/parameters/climate_udeb.rs */
 } rscm_b200_component_kind;
 
 /* GridType — crates/rscm-core/src/component.rs:56-64 */
@@ -68,6 +72,16 @@ typedef enum { RSCM_B200_SRC_EXOGENOUS = 0, RSCM_B200_SRC_OWN_STATE = 1, RSCM_B2
  *   GHG_FORCING  : method(0 Ipcctar,1 Olbl), co2_pi, ch4_pi, n2o_pi, delq2xco2, ch4_radeff,
  *                  n2o_radeff, olbl_co2_a1,b1,c1,d1, olbl_ch4_a3,b3,d3, olbl_n2o_a2,b2,c2,d2,
  *                  adjust_co2, adjust_ch4, adjust_n2o
+ *   OZONE_FORCING: eesc_reference, strat_o3_scale, strat_cl_exponent, trop_radeff, trop_oz_ch4,
+ *                  trop_oz_nox, trop_oz_co, trop_oz_voc, ch4_pi, nox_pi, co_pi, nmvoc_pi,
+ *                  temp_feedback_scale
+ *   AEROSOL_DIRECT: sox/bc/oc/nitrate_coefficient, sox_regional[4], bc_regional[4], oc_regional[4],
+ *                  nitrate_regional[4], sox_pi, bc_pi, oc_pi, nox_pi, harmonize, harmonize_year,
+ *                  harmonize_target
+ *   AEROSOL_INDIRECT: cloud_albedo_coefficient, reference_burden, sox_weight, oc_weight, sox_pi,
+ *                  oc_pi, harmonize, harmonize_year, harmonize_target
+ *   CLIMATE_UDEB : the fields of ClimateUDEBParameters in declaration order (rf_regions_co2
+ *                  expanded to 4 values, booleans/enums as 0/1/2), see rscm_b200/magicc.py
  */
 typedef struct {
     int32_t kind;     /* rscm_b200_component_kind */

@@ -88,3 +88,96 @@ static const orc_def ghg_defs[] = {
 };
 const orc_kind_info orc_kind_ghg_forcing = {ORC_GHG_FORCING, "GhgForcing", 6, ghg_defs, G_NPARAM,
                                             ghg_solve, 0, NULL};
+
+/* ------------------------------------------------------------------------- */
+/* OzoneForcing — crates/rscm-magicc/src/forcing/ozone.rs                     */
+/* params (parameters/ozone_forcing.rs field order): eesc_reference,          */
+/*  strat_o3_scale, strat_cl_exponent, trop_radeff, trop_oz_ch4, trop_oz_nox, */
+/*  trop_oz_co, trop_oz_voc, ch4_pi, nox_pi, co_pi, nmvoc_pi,                 */
+/*  temp_feedback_scale                                                       */
+/* ------------------------------------------------------------------------- */
+static int ozone_solve(const double *p, orc_ctx *c, double t0, double t1, double *out, void *st)
+{
+    (void)t0; (void)t1; (void)st;
+    const double eesc = orc_in_get(c, 0, 0), ch4 = orc_in_get(c, 1, 0), nox = orc_in_get(c, 2, 0);
+    const double co = orc_in_get(c, 3, 0), nmvoc = orc_in_get(c, 4, 0), temperature = orc_in_get(c, 5, 0);
+    /* calculate_strat_forcing — ozone.rs:187-203 */
+    const double delta_eesc = eesc - p[0];
+    out[0] = (delta_eesc <= 0.0) ? 0.0 : p[1] * pow(delta_eesc / 100.0, p[2]);
+    /* calculate_trop_forcing — ozone.rs:234-262 */
+    const double ch4_term = (ch4 > 0.0 && p[8] > 0.0) ? p[4] * log(ch4 / p[8]) : 0.0;
+    const double precursor = p[5] * (nox - p[9]) + p[6] * (co - p[10]) + p[7] * (nmvoc - p[11]);
+    out[1] = p[3] * (ch4_term + precursor);
+    out[2] = p[12] * temperature;
+    return 0;
+}
+static const orc_def ozone_defs[] = {
+    {"EESC", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Atmospheric Concentration|CH4", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Emissions|NOx", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Emissions|CO", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Emissions|NMVOC", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Surface Temperature", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Effective Radiative Forcing|O3|Stratospheric", ORC_REQ_OUTPUT, ORC_GRID_SCALAR},
+    {"Effective Radiative Forcing|O3|Tropospheric", ORC_REQ_OUTPUT, ORC_GRID_SCALAR},
+    {"Effective Radiative Forcing|O3|Temperature Feedback", ORC_REQ_OUTPUT, ORC_GRID_SCALAR},
+};
+const orc_kind_info orc_kind_ozone_forcing = {ORC_OZONE_FORCING, "OzoneForcing", 9, ozone_defs, 13, ozone_solve, 0, NULL};
+
+/* ------------------------------------------------------------------------- */
+/* AerosolDirect — crates/rscm-magicc/src/forcing/aerosol_direct.rs           */
+/* params: sox_coefficient, bc_coefficient, oc_coefficient,                   */
+/*  nitrate_coefficient, sox_regional[4], bc_regional[4], oc_regional[4],     */
+/*  nitrate_regional[4], sox_pi, bc_pi, oc_pi, nox_pi, harmonize,             */
+/*  harmonize_year, harmonize_target (the last three are carried, unused by   */
+/*  the reference's solve)                                                    */
+/* ------------------------------------------------------------------------- */
+static int aerosol_direct_solve(const double *p, orc_ctx *c, double t0, double t1, double *out, void *st)
+{
+    (void)t0; (void)t1; (void)st;
+    const double sox = orc_in_get(c, 0, 0), bc = orc_in_get(c, 1, 0), oc = orc_in_get(c, 2, 0), nox = orc_in_get(c, 3, 0);
+    /* calculate_species_forcing — :150-170 */
+    const double f_sox = p[0] * (sox - p[20]), f_bc = p[1] * (bc - p[21]);
+    const double f_oc = p[2] * (oc - p[22]), f_nit = p[3] * (nox - p[23]);
+    const double total = f_sox + f_bc + f_oc + f_nit;
+    /* distribute_regional — :172-192 */
+    if (fabs(total) < 1e-15) { for (int i = 0; i < 4; ++i) out[i] = 0.0; return 0; }
+    const double total_abs = fabs(f_sox) + fabs(f_bc) + fabs(f_oc) + fabs(f_nit);
+    if (total_abs < 1e-15) { for (int i = 0; i < 4; ++i) out[i] = total / 4.0; return 0; }
+    for (int i = 0; i < 4; ++i) {
+        const double pattern = (fabs(f_sox) * p[4 + i] + fabs(f_bc) * p[8 + i] + fabs(f_oc) * p[12 + i] + fabs(f_nit) * p[16 + i]) / total_abs;
+        out[i] = total * pattern;
+    }
+    return 0;
+}
+static const orc_def aerosol_direct_defs[] = {
+    {"Emissions|SOx", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Emissions|BC", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Emissions|OC", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Emissions|NOx", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Effective Radiative Forcing|Aerosol|Direct", ORC_REQ_OUTPUT, ORC_GRID_FOUR_BOX},
+};
+const orc_kind_info orc_kind_aerosol_direct = {ORC_AEROSOL_DIRECT, "AerosolDirect", 5, aerosol_direct_defs, 27, aerosol_direct_solve, 0, NULL};
+
+/* ------------------------------------------------------------------------- */
+/* AerosolIndirect — crates/rscm-magicc/src/forcing/aerosol_indirect.rs       */
+/* params: cloud_albedo_coefficient, reference_burden, sox_weight, oc_weight, */
+/*  sox_pi, oc_pi, harmonize, harmonize_year, harmonize_target                */
+/* ------------------------------------------------------------------------- */
+static int aerosol_indirect_solve(const double *p, orc_ctx *c, double t0, double t1, double *out, void *st)
+{
+    (void)t0; (void)t1; (void)st;
+    const double sox = orc_in_get(c, 0, 0), oc = orc_in_get(c, 1, 0);
+    /* calculate_cloud_albedo — :152-188 */
+    const double burden = p[2] * sox + p[3] * oc;
+    const double burden_pi = p[2] * p[4] + p[3] * p[5];
+    const double delta = burden - burden_pi;
+    out[0] = (delta <= 0.0) ? 0.0 : p[0] * log(1.0 + delta / p[1]);
+    return 0;
+}
+static const orc_def aerosol_indirect_defs[] = {
+    {"Emissions|SOx", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Emissions|OC", ORC_REQ_INPUT, ORC_GRID_SCALAR},
+    {"Effective Radiative Forcing|Aerosol|Indirect", ORC_REQ_OUTPUT, ORC_GRID_SCALAR},
+};
+const orc_kind_info orc_kind_aerosol_indirect = {ORC_AEROSOL_INDIRECT, "AerosolIndirect", 3, aerosol_indirect_defs, 9, aerosol_indirect_solve, 0, NULL};

@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "liboracle.so")
 
 TWO_LAYER, CARBON_CYCLE, CO2_ERF, GHG_FORCING = 1, 2, 3, 5
+OZONE_FORCING, AEROSOL_DIRECT, AEROSOL_INDIRECT, CLIMATE_UDEB = 6, 7, 8, 9
 SCALAR, FOUR_BOX, HEMISPHERIC = 0, 1, 2
 AGG_SUM, AGG_MEAN, AGG_WEIGHTED = 0, 1, 2
 

@@ -135,5 +135,9 @@ int orc_rk4(orc_rhs f, const void *self, int dim, double t0, double t1, double h
 
 /* magicc kinds, registered from magicc_*.c */
 extern const orc_kind_info orc_kind_ghg_forcing;
+extern const orc_kind_info orc_kind_ozone_forcing;
+extern const orc_kind_info orc_kind_aerosol_direct;
+extern const orc_kind_info orc_kind_aerosol_indirect;
+extern const orc_kind_info orc_kind_climate_udeb;
 
 #endif

@@ -89,11 +89,12 @@ double orc_in_at(const orc_ctx *c, int i, int region, int index)
          * FourBoxGrid::aggregate_global (spatial/four_box.rs:146) */
         const double *w = m->w_fourbox;
         double s = 0.0;
-        int any = 0;
         for (int r = 0; r < 4; ++r) {
-            if (!isnan(row[r])) { s += row[r] * w[r]; any = 1; }
+            /* custom weights (with_grid_weights): NaN terms are skipped; default grid:
+             * aggregate_global is a plain sum of v*w, NaN propagates */
+            if (m->has_w_fourbox && isnan(row[r])) continue;
+            s += row[r] * w[r];
         }
-        (void)any;
         return s * k;
     }
     if (var->grid == ORC_GRID_FOUR_BOX && want == ORC_GRID_HEMISPHERIC) {
@@ -104,8 +105,10 @@ double orc_in_at(const orc_ctx *c, int i, int region, int index)
     if (var->grid == ORC_GRID_HEMISPHERIC && want == ORC_GRID_SCALAR) {
         const double *w = m->w_hemi;
         double s = 0.0;
-        for (int r = 0; r < 2; ++r)
-            if (!isnan(row[r])) s += row[r] * w[r];
+        for (int r = 0; r < 2; ++r) {
+            if (m->has_w_hemi && isnan(row[r])) continue;
+            s += row[r] * w[r];
+        }
         return s * k;
     }
     return NAN; /* broadcast (coarse->fine) is rejected at build */
@@ -325,6 +328,10 @@ const orc_kind_info *orc_kind_lookup(int kind)
     case ORC_CO2_ERF: return &kind_co2_erf;
     case ORC_AGGREGATOR: return &kind_aggregator;
     case ORC_GHG_FORCING: return &orc_kind_ghg_forcing;
+    case ORC_OZONE_FORCING: return &orc_kind_ozone_forcing;
+    case ORC_AEROSOL_DIRECT: return &orc_kind_aerosol_direct;
+    case ORC_AEROSOL_INDIRECT: return &orc_kind_aerosol_indirect;
+    case ORC_CLIMATE_UDEB: return &orc_kind_climate_udeb;
     default: return NULL;
     }
 }

@@ -58,6 +58,7 @@ enum {
     ORC_OZONE_FORCING = 6,
     ORC_AEROSOL_DIRECT = 7,
     ORC_AEROSOL_INDIRECT = 8,
+    ORC_CLIMATE_UDEB = 9,  /* params: see magicc_climate.c */
     ORC_KIND_MAX = 32
 };
 

@@ -18,6 +18,25 @@
 
 namespace rscm_dev {
 
+constexpr int BLOCK = 128; // threads per CTA = stride of the per-thread shared-memory scratch
+
+// What a component's solve sees beyond its own operands.
+template <class R> struct StepCtx {
+    const int *nsub;      // RK4 sub-step tables [n_rk][Tpad] (shared memory)
+    const double *bounds; // time bounds (shared memory; valid when Prog::NEEDS_TIME)
+    const double *ctab;   // per-graph constant tables (shared memory)
+    R *sm;                // this thread's shared-memory scratch: element j at sm[j * BLOCK]
+    double *scratch;      // this run's global scratch: element j at scratch[j * runs]
+    long long runs;
+    int Tpad;
+    int N;                // current time index
+};
+
+// Per-node literals the emitter passes: RK4 table row, offsets into ctab / sm / scratch.
+struct NodeRef {
+    int rk, ctab, sm, scr;
+};
+
 template <class R> __device__ __forceinline__ R r_exp(R x);
 template <> __device__ __forceinline__ double r_exp<double>(double x) { return exp(x); }
 template <> __device__ __forceinline__ float r_exp<float>(float x) { return expf(x); }
@@ -73,8 +92,9 @@ __device__ __forceinline__ void two_layer_rhs(R k0, R k1, R k2, R k3, R eta_cd, 
 }
 
 template <class R>
-__device__ __forceinline__ bool two_layer_solve(const R *, const R *D, const R *in, R *out, int nsub)
+__device__ __forceinline__ bool two_layer_solve(const R *, const R *D, const R *in, R *out, const StepCtx<R> &cx, R *, NodeRef nr)
 {
+    const int nsub = cx.nsub[nr.rk * cx.Tpad + cx.N];
     if (nsub < 0) return false; // get_last_step assertion (ivp/mod.rs:94-97) would fire
     const R k1 = D[0], k2 = D[1], k3 = D[2], eta_cd = D[4];
     const R k0 = in[0] * D[3]; // F / Cs, F frozen over the step
@@ -116,8 +136,9 @@ __device__ __forceinline__ void carbon_cycle_prepare(const R *P, R *D)
 }
 
 template <class R>
-__device__ __forceinline__ bool carbon_cycle_solve(const R *P, const R *D, const R *in, R *out, int nsub)
+__device__ __forceinline__ bool carbon_cycle_solve(const R *P, const R *D, const R *in, R *out, const StepCtx<R> &cx, R *, NodeRef nr)
 {
+    const int nsub = cx.nsub[nr.rk * cx.Tpad + cx.N];
     if (nsub < 0) return false;
     const R gtc = R(2.13); // GTC_PER_PPM, crates/rscm-components/src/constants.rs:37
     const R conc_pi = P[1], alpha = P[2], h = P[3];
@@ -168,7 +189,7 @@ __device__ __forceinline__ void co2_erf_prepare(const R *P, R *D)
 }
 
 template <class R>
-__device__ __forceinline__ bool co2_erf_solve(const R *P, const R *D, const R *in, R *out, int)
+__device__ __forceinline__ bool co2_erf_solve(const R *P, const R *D, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
 {
     out[0] = D[0] * r_log<R>(R(1) + (in[0] - P[1]) * D[1]);
     return true;
@@ -191,7 +212,7 @@ template <class R> __device__ __forceinline__ R ghg_overlap_f(R ch4, R n2o)
 }
 
 template <class R>
-__device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *, const R *in, R *out, int)
+__device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
 {
     const R co2 = in[0], ch4 = in[1], n2o = in[2];
     R co2_raw, ch4_raw, n2o_raw;
@@ -218,6 +239,70 @@ __device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *, const R
     out[0] = co2_raw * P[18];
     out[1] = ch4_raw * P[19];
     out[2] = n2o_raw * P[20];
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// OzoneForcing — crates/rscm-magicc/src/forcing/ozone.rs:187-262
+//   P: eesc_reference, strat_o3_scale, strat_cl_exponent, trop_radeff, trop_oz_ch4, trop_oz_nox,
+//      trop_oz_co, trop_oz_voc, ch4_pi, nox_pi, co_pi, nmvoc_pi, temp_feedback_scale
+//   in: EESC, CH4, NOx, CO, NMVOC, temperature    out: strat, trop, temperature-feedback ERF
+// ---------------------------------------------------------------------------
+template <class R> __device__ __forceinline__ void ozone_forcing_prepare(const R *, R *D) { D[0] = R(0); }
+
+template <class R>
+__device__ __forceinline__ bool ozone_forcing_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
+{
+    const R delta_eesc = in[0] - P[0];
+    out[0] = (delta_eesc <= R(0)) ? R(0) : P[1] * r_pow<R>(delta_eesc / R(100), P[2]);
+    const R ch4_term = (in[1] > R(0) && P[8] > R(0)) ? P[4] * r_log<R>(in[1] / P[8]) : R(0);
+    const R precursor = P[5] * (in[2] - P[9]) + P[6] * (in[3] - P[10]) + P[7] * (in[4] - P[11]);
+    out[1] = P[3] * (ch4_term + precursor);
+    out[2] = P[12] * in[5];
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// AerosolDirect — crates/rscm-magicc/src/forcing/aerosol_direct.rs:150-192 (FourBox output)
+//   P: 4 species coefficients, 4 x regional[4] (SOx, BC, OC, nitrate), sox_pi, bc_pi, oc_pi, nox_pi,
+//      harmonize, harmonize_year, harmonize_target (carried; unused by the reference's solve)
+// ---------------------------------------------------------------------------
+template <class R> __device__ __forceinline__ void aerosol_direct_prepare(const R *, R *D) { D[0] = R(0); }
+
+template <class R> __device__ __forceinline__ R r_abs(R x) { return x < R(0) ? -x : x; }
+
+template <class R>
+__device__ __forceinline__ bool aerosol_direct_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
+{
+    const R f_sox = P[0] * (in[0] - P[20]), f_bc = P[1] * (in[1] - P[21]);
+    const R f_oc = P[2] * (in[2] - P[22]), f_nit = P[3] * (in[3] - P[23]);
+    const R total = f_sox + f_bc + f_oc + f_nit;
+    const R total_abs = r_abs(f_sox) + r_abs(f_bc) + r_abs(f_oc) + r_abs(f_nit);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const R pattern = (r_abs(f_sox) * P[4 + i] + r_abs(f_bc) * P[8 + i] + r_abs(f_oc) * P[12 + i] +
+                           r_abs(f_nit) * P[16 + i]) / total_abs;
+        R v = total * pattern;
+        if (total_abs < R(1e-15)) v = total / R(4);
+        if (r_abs(total) < R(1e-15)) v = R(0);
+        out[i] = v;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// AerosolIndirect — crates/rscm-magicc/src/forcing/aerosol_indirect.rs:152-188
+//   P: cloud_albedo_coefficient, reference_burden, sox_weight, oc_weight, sox_pi, oc_pi, harmonize*
+// ---------------------------------------------------------------------------
+template <class R> __device__ __forceinline__ void aerosol_indirect_prepare(const R *, R *D) { D[0] = R(0); }
+
+template <class R>
+__device__ __forceinline__ bool aerosol_indirect_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
+{
+    const R burden = P[2] * in[0] + P[3] * in[1];
+    const R burden_pi = P[2] * P[4] + P[3] * P[5];
+    const R delta = burden - burden_pi;
+    out[0] = (delta <= R(0)) ? R(0) : P[0] * r_log<R>(R(1) + delta / P[1]);
     return true;
 }
 
@@ -259,7 +344,18 @@ __device__ __forceinline__ R agg_weighted(const R (&v)[N], const R (&w)[N])
     return cnt ? s : r_nan<R>();
 }
 
-// read transform FourBox/Hemispheric -> Scalar: NaN regions skipped, no renormalisation
+// read transform with the grid's default weights: aggregate_global = plain sum of v*w (NaN propagates)
+template <class R, int N>
+__device__ __forceinline__ R read_plain(const R (&v)[N], const R (&w)[N])
+{
+    R s = R(0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) s += v[i] * w[i];
+    return s;
+}
+
+// read transform FourBox/Hemispheric -> Scalar with custom weights (ModelBuilder::with_grid_weights):
+// NaN regions skipped, no renormalisation
 template <class R, int N>
 __device__ __forceinline__ R read_weighted(const R (&v)[N], const R (&w)[N])
 {

@@ -37,15 +37,22 @@ cudaError_t launch_prog(int dtype, bool write, bool logp, dim3 grid, size_t smem
 {
     using namespace rscm_dev;
     const dim3 block(BLOCK);
+#define RSCM_LAUNCH(R, W, L)                                                                                                   \
+    do {                                                                                                                       \
+        if (smem > 48u * 1024u)                                                                                                \
+            cudaFuncSetAttribute(ensemble_kernel<R, Prog, W, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+        ensemble_kernel<R, Prog, W, L><<<grid, block, smem, st>>>(a);                                                          \
+    } while (0)
     if (dtype == 0) {
-        if (write && !logp) ensemble_kernel<double, Prog, true, false><<<grid, block, smem, st>>>(a);
-        else if (!write && logp) ensemble_kernel<double, Prog, false, true><<<grid, block, smem, st>>>(a);
-        else ensemble_kernel<double, Prog, true, true><<<grid, block, smem, st>>>(a);
+        if (write && !logp) RSCM_LAUNCH(double, true, false);
+        else if (!write && logp) RSCM_LAUNCH(double, false, true);
+        else RSCM_LAUNCH(double, true, true);
     } else {
-        if (write && !logp) ensemble_kernel<float, Prog, true, false><<<grid, block, smem, st>>>(a);
-        else if (!write && logp) ensemble_kernel<float, Prog, false, true><<<grid, block, smem, st>>>(a);
-        else ensemble_kernel<float, Prog, true, true><<<grid, block, smem, st>>>(a);
+        if (write && !logp) RSCM_LAUNCH(float, true, false);
+        else if (!write && logp) RSCM_LAUNCH(float, false, true);
+        else RSCM_LAUNCH(float, true, true);
     }
+#undef RSCM_LAUNCH
     return cudaGetLastError();
 }
 
@@ -86,6 +93,9 @@ struct rscm_b200_ensemble {
     double *d_exo = nullptr;
     int64_t exo_capacity_S = 0;
     int *d_nsub = nullptr;
+    double *d_bounds = nullptr, *d_ctab = nullptr;
+    double *d_scratch[2] = {nullptr, nullptr};
+    int64_t cap_scratch[2] = {0, 0};
     double *d_obs = nullptr;
     rscm_dev::PriorDev *d_priors = nullptr;
     rscm_dev::BlockPartial *d_partials = nullptr;
@@ -163,7 +173,10 @@ size_t smem_bytes(const rscm_b200_ensemble *h, bool logp)
     size_t b = 16;
     b += static_cast<size_t>(h->g.n_exo_rows) * h->Tpad * 8;
     if (logp) b += static_cast<size_t>(2 * h->n_obs_rows) * h->Tpad * 8;
+    if (h->g.needs_time) b += static_cast<size_t>(h->Tpad + 4) * 8;
+    b += h->g.ctab.size() * 8;
     b += static_cast<size_t>(h->g.n_rk) * h->Tpad * 4;
+    b += static_cast<size_t>(h->g.n_smem) * rscm_dev::BLOCK * (h->dtype ? 4 : 8);
     return b;
 }
 
@@ -207,6 +220,22 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     a.Tpad = h->Tpad;
     a.exo = h->d_exo;
     a.nsub = h->d_nsub;
+    a.bounds = h->d_bounds;
+    a.ctab = h->d_ctab;
+    a.n_ctab = static_cast<int>(g.ctab.size());
+    if (g.n_scratch_rows > 0) {
+        // global scratch of stateful components, one buffer per launch stream slot
+        const int64_t need = static_cast<int64_t>(g.n_scratch_rows) * S * M;
+        const int slot = (st == h->streams[1] && st) ? 1 : 0;
+        if (need > h->cap_scratch[slot]) {
+            if (h->d_scratch[slot]) cudaFree(h->d_scratch[slot]);
+            h->d_scratch[slot] = nullptr;
+            h->cap_scratch[slot] = 0;
+            CU(cudaMalloc(&h->d_scratch[slot], static_cast<size_t>(need) * 8));
+            h->cap_scratch[slot] = need;
+        }
+        a.scratch = h->d_scratch[slot];
+    }
     a.obs = h->d_obs;
     a.n_exo_rows = g.n_exo_rows;
     a.n_rk = g.n_rk;
@@ -376,6 +405,16 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
             return fail(nullptr, RSCM_B200_ECUDA, m);
         }
     }
+    if (g.needs_time) {
+        std::vector<double> b(static_cast<size_t>(h->Tpad) + 4, 0.0);
+        for (int t = 0; t <= g.T; ++t) b[t] = g.bounds[t];
+        cudaMalloc(&h->d_bounds, b.size() * 8);
+        cudaMemcpy(h->d_bounds, b.data(), b.size() * 8, cudaMemcpyHostToDevice);
+    }
+    if (!g.ctab.empty()) {
+        cudaMalloc(&h->d_ctab, g.ctab.size() * 8);
+        cudaMemcpy(h->d_ctab, g.ctab.data(), g.ctab.size() * 8, cudaMemcpyHostToDevice);
+    }
     // scenario row map: user layout [S][exo var][T][R] -> staged rows
     if (g.n_exo_rows > 0) {
         std::vector<int> off(g.n_exo_rows), stride(g.n_exo_rows);
@@ -410,6 +449,7 @@ void rscm_b200_ensemble_destroy(rscm_b200_ensemble *h)
 {
     if (!h) return;
     cudaFree(h->d_exo); cudaFree(h->d_nsub); cudaFree(h->d_obs); cudaFree(h->d_priors); cudaFree(h->d_partials);
+    cudaFree(h->d_bounds); cudaFree(h->d_ctab); cudaFree(h->d_scratch[0]); cudaFree(h->d_scratch[1]);
     cudaFree(h->d_ticket); cudaFree(h->d_row_off); cudaFree(h->d_row_stride); cudaFree(h->d_scen);
     cudaFree(h->d_logpost); cudaFree(h->d_summary);
     for (int i = 0; i < 2; ++i) {

@@ -15,6 +15,54 @@ namespace rscm {
 // (crates/rscm-macros/src/lib.rs:356-678) restated per kind.  Order of defs =
 // inputs, outputs, states (lib.rs:630-636).
 // ---------------------------------------------------------------------------
+// ClimateUDEB per-graph tables: af_top[n], af_bottom[n], af_diff[n] (compute_area_factors /
+// ocean_area_at_depth, crates/rscm-magicc/src/parameters/climate_udeb.rs) and the initial ocean profile of both
+// hemispheres (initial_ocean_profile, same file; CMIP5 defaults or the analytical exponential profile).
+#include "cmip5_profiles.inc"
+static std::vector<double> udeb_const_table(const std::vector<double> &p, std::string &err)
+{
+    const int n = static_cast<int>(p[0]);
+    if (n < 2 || n > 50 || p[0] != n) { err = "ClimateUDEB: n_layers must be an integer in [2, 50]"; return {}; }
+    const int steps = static_cast<int>(p[35]);
+    if (steps < 1 || p[35] != steps) { err = "ClimateUDEB: steps_per_year must be a positive integer"; return {}; }
+    const double mld = p[1], dz = p[2], dda = p[21];
+    auto area_at = [&](double depth) {
+        static const double D[12] = {0.0, 200.0, 500.0, 1000.0, 1500.0, 2000.0, 2500.0, 3000.0, 3500.0, 4000.0, 4500.0, 5000.0};
+        static const double A[12] = {1.0, 0.975, 0.95, 0.92, 0.91, 0.87, 0.81, 0.72, 0.55, 0.38, 0.18, 0.05};
+        double hydro;
+        if (depth <= D[0]) hydro = A[0];
+        else if (depth >= D[11]) hydro = A[11];
+        else {
+            hydro = A[0];
+            for (int i = 1; i < 12; ++i)
+                if (depth <= D[i]) { hydro = A[i - 1] + (depth - D[i - 1]) / (D[i] - D[i - 1]) * (A[i] - A[i - 1]); break; }
+        }
+        return 1.0 + dda * (hydro - 1.0);
+    };
+    std::vector<double> t(5 * n, 0.0);
+    for (int l = 0; l < n; ++l) {
+        double zt, zb;
+        if (l == 0) { zt = 0.0; zb = mld; }
+        else { zt = mld + (static_cast<double>(l) - 1.0) * dz; zb = zt + dz; }
+        const double at = area_at(zt), ab = area_at(zb), avg = (at + ab) / 2.0;
+        t[l] = at / avg;
+        t[n + l] = ab / avg;
+        t[2 * n + l] = (at - ab) / avg;
+    }
+    for (int h = 0; h < 2; ++h) {
+        for (int l = 0; l < n; ++l) {
+            double v;
+            if (p[34] == 2.0) v = (h == 0 ? CMIP5_NH : CMIP5_SH)[l < 50 ? l : 49];
+            else {
+                const double kap = p[3] * 3155.76;
+                v = (l == 0) ? 17.2 : 1.0 + (17.2 - 1.0) * std::exp(-p[6] * ((static_cast<double>(l) - 1.0) * dz + 0.5 * dz) / kap);
+            }
+            t[(3 + h) * n + l] = v;
+        }
+    }
+    return t;
+}
+
 static const std::vector<KindInfo> &kinds()
 {
     static const std::vector<KindInfo> k = {
@@ -53,6 +101,60 @@ static const std::vector<KindInfo> &kinds()
           "olbl_ch4_d3", "olbl_n2o_a2", "olbl_n2o_b2", "olbl_n2o_c2", "olbl_n2o_d2", "adjust_co2",
           "adjust_ch4", "adjust_n2o"},
          1, -2, {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 40},
+        {RSCM_B200_OZONE_FORCING, "OzoneForcing", "ozone_forcing",
+         // crates/rscm-magicc/src/forcing/ozone.rs (derive block)
+         {{"EESC", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Atmospheric Concentration|CH4", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|NOx", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|CO", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|NMVOC", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Surface Temperature", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|O3|Stratospheric", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|O3|Tropospheric", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|O3|Temperature Feedback", REQ_OUTPUT, RSCM_B200_SCALAR}},
+         {"eesc_reference", "strat_o3_scale", "strat_cl_exponent", "trop_radeff", "trop_oz_ch4", "trop_oz_nox", "trop_oz_co",
+          "trop_oz_voc", "ch4_pi", "nox_pi", "co_pi", "nmvoc_pi", "temp_feedback_scale"},
+         1, -2, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 16},
+        {RSCM_B200_AEROSOL_DIRECT, "AerosolDirect", "aerosol_direct",
+         // crates/rscm-magicc/src/forcing/aerosol_direct.rs (derive block); FourBox output
+         {{"Emissions|SOx", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|BC", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|OC", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|NOx", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|Aerosol|Direct", REQ_OUTPUT, RSCM_B200_FOUR_BOX}},
+         {"sox_coefficient", "bc_coefficient", "oc_coefficient", "nitrate_coefficient",
+          "sox_regional_0", "sox_regional_1", "sox_regional_2", "sox_regional_3",
+          "bc_regional_0", "bc_regional_1", "bc_regional_2", "bc_regional_3",
+          "oc_regional_0", "oc_regional_1", "oc_regional_2", "oc_regional_3",
+          "nitrate_regional_0", "nitrate_regional_1", "nitrate_regional_2", "nitrate_regional_3",
+          "sox_pi", "bc_pi", "oc_pi", "nox_pi", "harmonize", "harmonize_year", "harmonize_target"},
+         1, -2, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0}, 24},
+        {RSCM_B200_AEROSOL_INDIRECT, "AerosolIndirect", "aerosol_indirect",
+         // crates/rscm-magicc/src/forcing/aerosol_indirect.rs (derive block)
+         {{"Emissions|SOx", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|OC", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Effective Radiative Forcing|Aerosol|Indirect", REQ_OUTPUT, RSCM_B200_SCALAR}},
+         {"cloud_albedo_coefficient", "reference_burden", "sox_weight", "oc_weight", "sox_pi", "oc_pi", "harmonize",
+          "harmonize_year", "harmonize_target"},
+         1, -2, {1, 1, 1, 1, 1, 1, 0, 0, 0}, 8},
+        {RSCM_B200_CLIMATE_UDEB, "ClimateUDEB", "climate_udeb",
+         // crates/rscm-magicc/src/climate/udeb/mod.rs (derive block): inputs, outputs, states
+         {{"Effective Radiative Forcing", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Heat Uptake", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Ocean Heat Content", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Sea Surface Temperature", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Surface Temperature", REQ_STATE, RSCM_B200_FOUR_BOX}},
+         {"n_layers", "mixed_layer_depth", "layer_thickness", "kappa", "kappa_min", "kappa_dkdt", "w_initial", "w_variable_fraction",
+          "w_threshold_temp_nh", "w_threshold_temp_sh", "ecs", "rf_2xco2", "rlo", "feedback_q_sensitivity", "feedback_cumt_sensitivity",
+          "feedback_cumt_period", "k_lo", "k_ns", "amplify_ocean_to_land", "nh_land_fraction", "sh_land_fraction", "depth_dependent_area",
+          "temp_adjust_alpha", "temp_adjust_gamma", "polar_sinking_ratio", "land_heat_capacity_enabled", "k_lg", "land_hc_eff_thickness",
+          "rf_regions_co2_0", "rf_regions_co2_1", "rf_regions_co2_2", "rf_regions_co2_3", "efficacy_apply", "prescribed_efficacy_co2",
+          "ocean_temp_profile", "steps_per_year", "max_temperature"},
+         1, -2,
+         // geometry / switches are per-graph (they size the shared-memory layout and the host-computed tables)
+         {0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 1},
+         96, /*n_state*/ 19, /*n_smem*/ 150, /*scratch_per_T*/ 1, /*needs_time*/ true,
+         /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table},
     };
     return k;
 }
@@ -135,7 +237,7 @@ static std::string input_expr(const Graph &g, const Node &n, int i, int r, bool 
         pre << "        const R rw" << id << "[4] = {" << lit(g.w_fourbox[0]) << ", " << lit(g.w_fourbox[1]) << ", "
             << lit(g.w_fourbox[2]) << ", " << lit(g.w_fourbox[3]) << "};\n";
         std::ostringstream s;
-        s << "rscm_dev::read_weighted<R, 4>(rv" << id << ", rw" << id << ")";
+        s << "rscm_dev::" << (g.custom_w_fourbox ? "read_weighted" : "read_plain") << "<R, 4>(rv" << id << ", rw" << id << ")";
         e = s.str();
     } else if (var.grid == RSCM_B200_FOUR_BOX && want == RSCM_B200_HEMISPHERIC) {
         // state/aggregating.rs:611-618
@@ -147,7 +249,7 @@ static std::string input_expr(const Graph &g, const Node &n, int i, int r, bool 
         pre << "        const R rv" << id << "[2] = {" << cell_ref(at_end, var.cell0) << ", " << cell_ref(at_end, var.cell0 + 1) << "};\n";
         pre << "        const R rw" << id << "[2] = {" << lit(g.w_hemi[0]) << ", " << lit(g.w_hemi[1]) << "};\n";
         std::ostringstream s;
-        s << "rscm_dev::read_weighted<R, 2>(rv" << id << ", rw" << id << ")";
+        s << "rscm_dev::" << (g.custom_w_hemi ? "read_weighted" : "read_plain") << "<R, 2>(rv" << id << ", rw" << id << ")";
         e = s.str();
     }
     if (n.in_factor[i] != 1.0) e = "(" + e + " * " + lit(n.in_factor[i]) + ")";
@@ -164,7 +266,11 @@ static void emit_program(Graph &g)
     for (const Node &n : g.nodes)
         if (n.kind != KIND_AGGREGATOR) weight += kind_info(n.kind)->reg_weight;
     // 8 CTAs of 128 threads per SM = 64 registers per thread; register-hungry programs get 4 (128 registers)
-    o << "    static constexpr int MIN_BLOCKS = " << (weight <= 32 ? 8 : 4) << ";\n";
+    // programs with per-thread shared-memory scratch are limited by shared memory, not registers
+    o << "    static constexpr int MIN_BLOCKS = " << (g.n_smem > 0 ? 1 : (weight <= 32 ? 8 : 4)) << ";\n";
+    o << "    static constexpr int NS = " << g.n_state << ";\n";
+    o << "    static constexpr int NSM = " << g.n_smem << ";\n";
+    o << "    static constexpr bool NEEDS_TIME = " << (g.needs_time ? "true" : "false") << ";\n";
     o << "    __host__ __device__ static constexpr int exo_row(int c) { return ";
     for (int c = 0; c < g.n_cells; ++c) {
         const Variable &v = g.vars[g.cell_var[c]];
@@ -190,9 +296,26 @@ static void emit_program(Graph &g)
         o << "        rscm_dev::" << k->dev_name << "_prepare<R>(P + " << n.param_base << ", D + " << n.derived_base << ");\n";
     }
     o << "    }\n";
-    o << "    template <class R> __device__ __forceinline__ static void step(const R *P, const R *D, const R *cur, R *nxt,\n"
-         "                                                                  const int *s_nsub, int Tpad, int N, unsigned &fail) {\n";
-    o << "        (void)P; (void)D; (void)cur; (void)s_nsub; (void)Tpad; (void)N; (void)fail;\n";
+    auto node_ref = [](const Node &n) {
+        std::ostringstream s;
+        s << "rscm_dev::NodeRef{" << (n.rk_table >= 0 ? n.rk_table : 0) << ", " << n.ctab_base << ", " << n.smem_base << ", "
+          << n.scratch_base << "}";
+        return s.str();
+    };
+    o << "    template <class R> __device__ __forceinline__ static void init_state(const R *P, const R *D, R *S,\n"
+         "                                                                        const rscm_dev::StepCtx<R> &cx) {\n";
+    o << "        (void)P; (void)D; (void)S; (void)cx;\n";
+    for (const Node &n : g.nodes) {
+        if (n.kind == KIND_AGGREGATOR) continue;
+        const KindInfo *k = kind_info(n.kind);
+        if (k->n_state == 0 && k->n_smem == 0) continue;
+        o << "        rscm_dev::" << k->dev_name << "_init_state<R>(P + " << n.param_base << ", D + " << n.derived_base << ", S + "
+          << n.state_base << ", cx, " << node_ref(n) << ");\n";
+    }
+    o << "    }\n";
+    o << "    template <class R> __device__ __forceinline__ static void step(const R *P, const R *D, const R *cur, R *nxt, R *S,\n"
+         "                                                                  const rscm_dev::StepCtx<R> &cx, unsigned &fail) {\n";
+    o << "        (void)P; (void)D; (void)cur; (void)S; (void)cx; (void)fail;\n";
     int tmp_id = 0;
     for (int ni : g.order) {
         const Node &n = g.nodes[ni];
@@ -220,12 +343,17 @@ static void emit_program(Graph &g)
         } else {
             const KindInfo *k = kind_info(n.kind);
             std::vector<std::string> in_exprs;
-            for (size_t i = 0; i < n.in_var.size(); ++i) {
+            // default access: one get() per input — UpstreamOutput -> at_end (always in range during run), else
+            // at_start (state/windows.rs:229-234); state inputs are read with at_start.  Kinds that call at_start /
+            // at_end explicitly (e.g. ClimateUDEB's erf_start / erf_end) list their accesses in in_access.
+            std::vector<std::pair<int, int>> access = k->in_access;
+            if (access.empty())
+                for (size_t i = 0; i < n.in_var.size(); ++i) access.push_back({static_cast<int>(i), 0});
+            for (const auto &ac : access) {
+                const int i = ac.first;
                 const int Rc = grid_regions(n.in_grid[i]);
-                // get(): UpstreamOutput -> at_end (always in range during run), else at_start
-                // (state/windows.rs:229-234); state inputs are read with at_start.
-                const bool at_end = n.in_src[i] == RSCM_B200_SRC_UPSTREAM;
-                for (int r = 0; r < Rc; ++r) in_exprs.push_back(input_expr(g, n, static_cast<int>(i), r, at_end, pre, tmp_id));
+                const bool at_end = ac.second == 2 || (ac.second == 0 && n.in_src[i] == RSCM_B200_SRC_UPSTREAM);
+                for (int r = 0; r < Rc; ++r) in_exprs.push_back(input_expr(g, n, i, r, at_end, pre, tmp_id));
             }
             int n_out_vals = 0;
             for (size_t i = 0; i < n.out_var.size(); ++i) n_out_vals += grid_regions(n.out_grid[i]);
@@ -236,10 +364,7 @@ static void emit_program(Graph &g)
             o << "};\n";
             o << "        R out[" << n_out_vals << "];\n";
             o << "        if (rscm_dev::" << k->dev_name << "_solve<R>(P + " << n.param_base << ", D + " << n.derived_base
-              << ", in, out, ";
-            if (n.rk_table >= 0) o << "s_nsub[" << n.rk_table << " * Tpad + N]";
-            else o << "0";
-            o << ")) {\n";
+              << ", in, out, cx, S + " << n.state_base << ", " << node_ref(n) << ")) {\n";
             int pos = 0;
             for (size_t i = 0; i < n.out_var.size(); ++i) {
                 const Variable &var = g.vars[n.out_var[i]];
@@ -283,8 +408,8 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
     g = Graph();
     g.T = d.n_times;
     g.bounds.assign(d.time_bounds, d.time_bounds + d.n_times + 1);
-    if (d.four_box_weights) std::memcpy(g.w_fourbox, d.four_box_weights, sizeof g.w_fourbox);
-    if (d.hemispheric_weights) std::memcpy(g.w_hemi, d.hemispheric_weights, sizeof g.w_hemi);
+    if (d.four_box_weights) { std::memcpy(g.w_fourbox, d.four_box_weights, sizeof g.w_fourbox); g.custom_w_fourbox = true; }
+    if (d.hemispheric_weights) { std::memcpy(g.w_hemi, d.hemispheric_weights, sizeof g.w_hemi); g.custom_w_hemi = true; }
 
     std::vector<std::string> agg_names;
     for (int i = 0; i < d.n_aggregates; ++i) agg_names.push_back(d.aggregates[i].name);
@@ -505,6 +630,26 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         }
         g.n_slots += static_cast<int>(n.params.size());
         g.n_derived += k->n_derived;
+        // stateful kinds: per-thread state, shared-memory scratch, global scratch, per-graph constant tables
+        n.state_base = g.n_state;
+        n.smem_base = g.n_smem;
+        n.scratch_base = g.n_scratch_rows;
+        n.ctab_base = static_cast<int>(g.ctab.size());
+        g.n_state += k->n_state;
+        g.n_smem += k->n_smem;
+        g.n_scratch_rows += k->scratch_per_T * g.T;
+        g.needs_time = g.needs_time || k->needs_time;
+        if (k->const_table) {
+            std::string terr;
+            const std::vector<double> tab = k->const_table(n.params, terr);
+            if (!terr.empty()) { err = terr; return false; }
+            g.ctab.insert(g.ctab.end(), tab.begin(), tab.end());
+        }
+        if (n.kind == RSCM_B200_CLIMATE_UDEB && n.params[34] != 2.0) {
+            // analytical initial profile depends on kappa and w_initial: they feed the host-computed table
+            g.slot_bindable[n.param_base + 3] = 0;
+            g.slot_bindable[n.param_base + 6] = 0;
+        }
         if (k->rk_step_param != -2) {
             const double h = k->rk_step_param >= 0 ? n.params[k->rk_step_param] : 0.1;
             n.rk_table = g.n_rk++;
@@ -513,6 +658,7 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
             g.rk_nsub.push_back(tab);
         }
     }
+    if (g.ctab.size() % 2) g.ctab.push_back(0.0); // keep every staged section a 16-byte multiple
     emit_program(g);
     return true;
 }
@@ -540,7 +686,7 @@ int Graph::resolve_slot(const std::string &slot, std::string &err) const
         if (want_index >= 0 && want_index != ni) continue;
         for (size_t p = 0; p < k->param_names.size(); ++p) {
             if (field != k->param_names[p]) continue;
-            if (!k->bindable[p]) { err = "parameter '" + slot + "' cannot vary per member"; return -1000000000; }
+            if (!slot_bindable[n.param_base + p]) { err = "parameter '" + slot + "' cannot vary per member"; return -1000000000; }
             return n.param_base + static_cast<int>(p);
         }
         err = "unknown field in '" + slot + "'";

@@ -35,6 +35,16 @@ struct KindInfo {
     int rk_step_param; // index of the RK4 step-size parameter, -1: fixed 0.1, -2: no RK4
     std::vector<int> bindable; // 1 if the parameter may be bound to a member column
     int reg_weight;            // rough register appetite; decides the kernel's min-CTAs-per-SM hint
+    // stateful kinds (ClimateUDEB, ...): sizes of the per-thread state the fused kernel provides
+    int n_state = 0;       // register/local values (R S[])
+    int n_smem = 0;        // per-thread shared-memory scratch values
+    int scratch_per_T = 0; // global scratch rows per time point (member-interleaved)
+    bool needs_time = false; // solve uses the time bounds
+    // input access override: (input index, mode) per `in[]` entry group; mode 0 = get(), 1 = at_start, 2 = at_end.
+    // empty = one get() per input (state inputs at_start)
+    std::vector<std::pair<int, int>> in_access = {};
+    // per-graph constant table computed on the host from the (non-bindable) geometry parameters
+    std::vector<double> (*const_table)(const std::vector<double> &params, std::string &err) = nullptr;
 };
 
 const KindInfo *kind_info(int kind);
@@ -59,6 +69,7 @@ struct Node {
     int param_base = 0;   // first parameter slot
     int derived_base = 0; // first derived-constant slot
     int rk_table = -1;    // row of the sub-step table
+    int state_base = 0, smem_base = 0, scratch_base = 0, ctab_base = 0; // offsets of this node's stateful storage
     std::vector<int> in_var, in_src, in_grid;
     std::vector<double> in_factor;
     std::vector<int> out_var, out_grid;
@@ -76,6 +87,9 @@ struct Graph {
     std::vector<int> order;     // node ids in execution order
     std::vector<int> exo_vars;  // variable ids, scenario order
     int n_cells = 0, n_slots = 0, n_derived = 0, n_exo_rows = 0, n_rk = 0;
+    int n_state = 0, n_smem = 0, n_scratch_rows = 0; // stateful components: totals (scratch rows already x T)
+    bool needs_time = false;
+    std::vector<double> ctab; // concatenated per-graph constant tables (even length)
     std::vector<double> slot_default;
     std::vector<int> slot_bindable;
     std::vector<int> cell_var, cell_region;
@@ -83,6 +97,7 @@ struct Graph {
     std::vector<double> bounds;
     double w_fourbox[4] = {0.25, 0.25, 0.25, 0.25};
     double w_hemi[2] = {0.5, 0.5};
+    bool custom_w_fourbox = false, custom_w_hemi = false; // set through ModelBuilder::with_grid_weights
     std::vector<std::vector<int>> rk_nsub; // [n_rk][T]
     std::string program_source;            // emitted Prog body (without the struct name)
     std::string signature;                 // canonical key = hash-free text of the program

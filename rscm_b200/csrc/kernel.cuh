@@ -18,6 +18,7 @@
 #pragma once
 // (no standard headers: this file is also compiled by NVRTC at run time)
 #include "components.cuh"
+#include "climate_udeb.cuh"
 #define RSCM_INF (__longlong_as_double(0x7ff0000000000000LL))
 
 namespace rscm_dev {
@@ -25,7 +26,6 @@ namespace rscm_dev {
 constexpr int MAX_SLOTS = 96;   // component parameter slots per program
 constexpr int MAX_CELLS = 48;   // scalar storage cells (variables x regions)
 constexpr int MAX_OBS_ROWS = 4; // dense observation tables (one per observed variable)
-constexpr int BLOCK = 128;
 
 struct PriorDev {
     int kind;
@@ -59,6 +59,10 @@ struct KArgs {
     const double *exo;   // [S][n_exo_rows][Tpad]
     const int *nsub;     // [n_rk][Tpad]   RK4 sub-steps per step; <0: get_last_step would assert
     const double *obs;   // [2][n_obs_rows][Tpad]: values then sigmas (sigma<=0: no observation)
+    const double *bounds; // [Tpad + 4] time bounds (T + 1 used), staged only for programs that need the time axis
+    const double *ctab;   // [n_ctab] per-graph constant tables of stateful components (host-computed)
+    double *scratch;      // [n_scratch][runs] member-interleaved global scratch of stateful components, or null
+    int n_ctab;
     int n_exo_rows, n_rk, n_obs_rows;
     int normalize;
     int obs_cell[MAX_OBS_ROWS];
@@ -184,16 +188,24 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     constexpr int NP = Prog::NP;
     constexpr int ND = Prog::ND;
 
+    // shared memory map (all sections 16-byte multiples):
+    //   mbarrier | exogenous rows | observation tables | time bounds | graph constant tables | RK4 sub-step tables |
+    //   per-thread scratch of stateful components ([Prog::NSM][BLOCK], conflict-free)
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
     double *s_exo = reinterpret_cast<double *>(smem + 16);
     double *s_obs = s_exo + static_cast<unsigned long long>(a.n_exo_rows) * a.Tpad;
-    int *s_nsub = reinterpret_cast<int *>(s_obs + static_cast<unsigned long long>(2 * a.n_obs_rows) * a.Tpad);
+    double *s_bounds = s_obs + static_cast<unsigned long long>(LOGP ? 2 * a.n_obs_rows : 0) * a.Tpad;
+    double *s_ctab = s_bounds + (Prog::NEEDS_TIME ? a.Tpad + 4 : 0);
+    int *s_nsub = reinterpret_cast<int *>(s_ctab + a.n_ctab);
+    R *s_thread = reinterpret_cast<R *>(s_nsub + static_cast<unsigned long long>(a.n_rk) * a.Tpad) + threadIdx.x;
 
     const unsigned exo_bytes = static_cast<unsigned>(a.n_exo_rows) * a.Tpad * 8u;
     const unsigned obs_bytes = LOGP ? static_cast<unsigned>(2 * a.n_obs_rows) * a.Tpad * 8u : 0u;
+    const unsigned bounds_bytes = Prog::NEEDS_TIME ? static_cast<unsigned>(a.Tpad + 4) * 8u : 0u;
+    const unsigned ctab_bytes = static_cast<unsigned>(a.n_ctab) * 8u;
     const unsigned nsub_bytes = static_cast<unsigned>(a.n_rk) * a.Tpad * 4u;
-    const unsigned total_bytes = exo_bytes + obs_bytes + nsub_bytes;
+    const unsigned total_bytes = exo_bytes + obs_bytes + bounds_bytes + ctab_bytes + nsub_bytes;
 
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -202,6 +214,8 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
         if (exo_bytes)
             tma_bulk_g2s(s_exo, a.exo + static_cast<unsigned long long>(blockIdx.y) * a.n_exo_rows * a.Tpad, exo_bytes, bar);
         if (obs_bytes) tma_bulk_g2s(s_obs, a.obs, obs_bytes, bar);
+        if (bounds_bytes) tma_bulk_g2s(s_bounds, a.bounds, bounds_bytes, bar);
+        if (ctab_bytes) tma_bulk_g2s(s_ctab, a.ctab, ctab_bytes, bar);
         if (nsub_bytes) tma_bulk_g2s(s_nsub, a.nsub, nsub_bytes, bar);
     }
 
@@ -238,6 +252,20 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     for (int c = 0; c < NC; ++c)
         if (Prog::exo_row(c) >= 0) cur[c] = static_cast<R>(s_exo[Prog::exo_row(c) * a.Tpad]);
 
+    // stateful components: small per-thread state in registers/local (S), large in the per-thread
+    // shared-memory scratch and the member-interleaved global scratch (cx.scratch[j*runs + run])
+    StepCtx<R> cx;
+    cx.nsub = s_nsub;
+    cx.bounds = s_bounds;
+    cx.ctab = s_ctab;
+    cx.sm = s_thread;
+    cx.scratch = a.scratch ? a.scratch + run : nullptr;
+    cx.runs = a.runs;
+    cx.Tpad = a.Tpad;
+    cx.N = 0;
+    R S[Prog::NS > 0 ? Prog::NS : 1];
+    Prog::template init_state<R>(P, D, S, cx);
+
     double ll[MAX_OBS_ROWS] = {0.0, 0.0, 0.0, 0.0};
     bool bad = false;
     unsigned fail = 0;
@@ -271,7 +299,8 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
             if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(s_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
             else nxt[c] = r_nan<R>();
         }
-        Prog::template step<R>(P, D, cur, nxt, s_nsub, a.Tpad, N, fail);
+        cx.N = N;
+        Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
 
         if (WRITE) {
             if (N + 1 == tnext && tnext < a.t_stop) { // block-uniform

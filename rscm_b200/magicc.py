@@ -1,9 +1,14 @@
-"""Mirror of ``rscm._lib.magicc`` (python/rscm/_lib/magicc.pyi) for the kinds with device code."""
+"""Mirror of ``rscm._lib.magicc`` (python/rscm/_lib/magicc.pyi) for the kinds with device code.
+
+Every builder accepts the reference's parameter dictionary (serde ``default`` semantics: missing keys take the
+defaults of ``crates/rscm-magicc/src/parameters/*.rs``) and flattens it into the C ABI's parameter block.
+"""
 
 from . import _ffi
 from ._builders import ComponentBuilder
+from .core import Component
 
-__all__ = ["GhgForcingBuilder"]
+__all__ = ["GhgForcingBuilder", "OzoneForcingBuilder", "AerosolDirectBuilder", "AerosolIndirectBuilder", "ClimateUDEBBuilder"]
 
 
 class GhgForcingBuilder(ComponentBuilder):
@@ -44,4 +49,91 @@ class GhgForcingBuilder(ComponentBuilder):
                 except KeyError:
                     raise ValueError(f"GhgForcing: unknown method {v!r}") from None
             return float(v)
+        return float(v)
+
+
+class OzoneForcingBuilder(ComponentBuilder):
+    """OzoneForcingParameters — crates/rscm-magicc/src/parameters/ozone_forcing.rs."""
+
+    KIND = _ffi.OZONE_FORCING
+    TYPE_NAME = "OzoneForcing"
+    FIELDS = (
+        ("eesc_reference", 1420.0), ("strat_o3_scale", -0.0043), ("strat_cl_exponent", 1.7), ("trop_radeff", 0.032),
+        ("trop_oz_ch4", 5.7), ("trop_oz_nox", 0.168), ("trop_oz_co", 0.00396), ("trop_oz_voc", 0.01008), ("ch4_pi", 700.0),
+        ("nox_pi", 0.0), ("co_pi", 0.0), ("nmvoc_pi", 0.0), ("temp_feedback_scale", -0.037),
+    )
+
+
+class _ArrayFieldsBuilder(ComponentBuilder):
+    """Builders whose reference parameter struct has `[f64; 4]` fields: they are flattened to name_0..name_3."""
+
+    ARRAYS: dict = {}
+
+    @classmethod
+    def from_parameters(cls, parameters: dict):
+        flat = {}
+        for k, v in parameters.items():
+            if k in cls.ARRAYS:
+                if len(v) != 4:
+                    raise ValueError(f"{cls.TYPE_NAME}: {k} needs 4 values")
+                for i, x in enumerate(v):
+                    flat[f"{k}_{i}"] = x
+            else:
+                flat[k] = v
+        return super().from_parameters(flat)
+
+
+class AerosolDirectBuilder(_ArrayFieldsBuilder):
+    """AerosolDirectParameters — crates/rscm-magicc/src/parameters/aerosol.rs."""
+
+    KIND = _ffi.AEROSOL_DIRECT
+    TYPE_NAME = "AerosolDirect"
+    ARRAYS = {"sox_regional": None, "bc_regional": None, "oc_regional": None, "nitrate_regional": None}
+    FIELDS = (
+        ("sox_coefficient", -0.0035), ("bc_coefficient", 0.0077), ("oc_coefficient", -0.002), ("nitrate_coefficient", -0.001),
+        *[(f"sox_regional_{i}", v) for i, v in enumerate([0.15, 0.55, 0.10, 0.20])],
+        *[(f"bc_regional_{i}", v) for i, v in enumerate([0.15, 0.50, 0.15, 0.20])],
+        *[(f"oc_regional_{i}", v) for i, v in enumerate([0.15, 0.45, 0.15, 0.25])],
+        *[(f"nitrate_regional_{i}", v) for i, v in enumerate([0.15, 0.50, 0.15, 0.20])],
+        ("sox_pi", 1.0), ("bc_pi", 2.5), ("oc_pi", 10.0), ("nox_pi", 10.0),
+        ("harmonize", 0.0), ("harmonize_year", 2019.0), ("harmonize_target", -0.22),
+    )
+
+
+class AerosolIndirectBuilder(ComponentBuilder):
+    """AerosolIndirectParameters — crates/rscm-magicc/src/parameters/aerosol.rs."""
+
+    KIND = _ffi.AEROSOL_INDIRECT
+    TYPE_NAME = "AerosolIndirect"
+    FIELDS = (
+        ("cloud_albedo_coefficient", -1.0), ("reference_burden", 50.0), ("sox_weight", 1.0), ("oc_weight", 0.3),
+        ("sox_pi", 1.0), ("oc_pi", 10.0), ("harmonize", 0.0), ("harmonize_year", 2019.0), ("harmonize_target", -0.89),
+    )
+
+
+class ClimateUDEBBuilder(_ArrayFieldsBuilder):
+    """ClimateUDEBParameters — crates/rscm-magicc/src/parameters/climate_udeb.rs:235-300 (defaults)."""
+
+    KIND = _ffi.CLIMATE_UDEB
+    TYPE_NAME = "ClimateUDEB"
+    ARRAYS = {"rf_regions_co2": None}
+    FIELDS = (
+        ("n_layers", 50), ("mixed_layer_depth", 60.0), ("layer_thickness", 100.0),
+        ("kappa", 0.75), ("kappa_min", 0.1), ("kappa_dkdt", -0.191),
+        ("w_initial", 3.5), ("w_variable_fraction", 0.7), ("w_threshold_temp_nh", 8.0), ("w_threshold_temp_sh", 8.0),
+        ("ecs", 3.0), ("rf_2xco2", 3.71), ("rlo", 1.317),
+        ("feedback_q_sensitivity", 7.84e-9), ("feedback_cumt_sensitivity", 0.08), ("feedback_cumt_period", 300.0),
+        ("k_lo", 1.44), ("k_ns", 0.31), ("amplify_ocean_to_land", 1.02),
+        ("nh_land_fraction", 0.42), ("sh_land_fraction", 0.21), ("depth_dependent_area", 1.0),
+        ("temp_adjust_alpha", 1.04), ("temp_adjust_gamma", -0.002), ("polar_sinking_ratio", 0.2),
+        ("land_heat_capacity_enabled", 1.0), ("k_lg", 0.1), ("land_hc_eff_thickness", 300.0),
+        ("rf_regions_co2_0", 1.4089), ("rf_regions_co2_1", 1.37045), ("rf_regions_co2_2", 1.43333), ("rf_regions_co2_3", 1.33257),
+        ("efficacy_apply", 0), ("prescribed_efficacy_co2", 1.0),
+        ("ocean_temp_profile", 2), ("steps_per_year", 12), ("max_temperature", 25.0),
+    )
+
+    def _value(self, name, default):
+        v = self._parameters.get(name, default)
+        if name == "ocean_temp_profile" and isinstance(v, str):
+            return {"analytical": 1.0, "cmip5": 2.0, "1": 1.0, "2": 2.0}[v.lower()]
         return float(v)

@@ -54,3 +54,38 @@ if __name__ == "__main__":
         keep = {k: cfg[k] for k in cfg if k.startswith("core_")}
         np.savez_compressed(os.path.join(HERE, f"ghg_forcing_{name[:2]}.npz"), config=json.dumps(keep), **data)
         print(name, {k: v.shape for k, v in data.items()}, keep)
+
+
+# ---- ClimateUDEB: tests/regression/data/ocean_udeb/*.csv (MAGICC7 global-mean Surface Temperature under
+# ABRUPT-2XCO2 step forcing; compared by tests/regression/test_ocean_udeb.py with phased 1-5 % tolerances) ----
+UDEB = "/root/reference/tests/regression/data/ocean_udeb"
+UDEB_SCENARIOS = ["01_diffusion_only", "02_constant_upwelling", "03_depth_dependent_area", "04_variable_upwelling",
+                  "05_temp_dependent_diffusivity", "06_ground_heat", "07_interhemispheric_exchange", "09_time_varying_ecs",
+                  "11_efficacy_ar6"]
+
+
+def load_udeb(name):
+    with open(os.path.join(UDEB, name + ".csv")) as f:
+        rows = list(csv.reader(f))
+    header = rows[0]
+    ivar, ireg = header.index("variable"), header.index("region")
+    tcols = [i for i, h in enumerate(header) if h[:4].isdigit()]
+    years = np.array([float(header[i][:4]) for i in tcols])
+    temp = None
+    for r in rows[1:]:
+        if r[ivar] == "Surface Temperature" and r[ireg] == "World":
+            temp = np.array([float(r[i]) for i in tcols])
+    with open(os.path.join(UDEB, name + "_config.json")) as f:
+        cfg = json.load(f)
+    return years, temp, {k: v for k, v in cfg.items() if k.startswith(("core_", "rf_efficacy"))}
+
+
+if __name__ == "__main__":
+    out = {}
+    for name in UDEB_SCENARIOS:
+        years, temp, cfg = load_udeb(name)
+        out[name + "/years"] = years
+        out[name + "/temp"] = temp
+        out[name + "/config"] = json.dumps(cfg)
+        print(name, years[0], years[-1], temp[-1], cfg)
+    np.savez_compressed(os.path.join(HERE, "ocean_udeb.npz"), **out)
