@@ -23,7 +23,7 @@
 
 namespace rscm_dev {
 
-constexpr int MAX_SLOTS = 96;   // component parameter slots per program
+constexpr int MAX_SLOTS = 160;  // component parameter slots per program (KArgs stays below the 4 KB parameter limit)
 constexpr int MAX_CELLS = 48;   // scalar storage cells (variables x regions)
 constexpr int MAX_OBS_ROWS = 4; // dense observation tables (one per observed variable)
 

@@ -139,3 +139,66 @@ def config5_observations(truth_temperature: np.ndarray, years: np.ndarray, sigma
         if 1850.0 <= y <= 2020.0:
             obs.append(("Surface Temperature", float(y), float(truth_temperature[i] + sigma * rng.standard_normal()), sigma))
     return obs
+
+
+# ---- config 4: MAGICC box components on the four-box grid ------------------------------------------------------
+CONFIG4_RANGES = {"ecs": (1.5, 4.5), "kappa": (0.5, 1.5), "rlo": (1.1, 1.5)}
+CONFIG4_BINDINGS = {"ecs": "ClimateUDEB.ecs", "kappa": "ClimateUDEB.kappa", "rlo": "ClimateUDEB.rlo"}
+CONFIG4_ERF_PARTS = [
+    "Effective Radiative Forcing|CO2", "Effective Radiative Forcing|CH4", "Effective Radiative Forcing|N2O",
+    "Effective Radiative Forcing|O3|Stratospheric", "Effective Radiative Forcing|O3|Tropospheric",
+    "Effective Radiative Forcing|O3|Temperature Feedback", "Effective Radiative Forcing|Aerosol|Direct",
+    "Effective Radiative Forcing|Aerosol|Indirect",
+]
+CONFIG4_OUTPUTS = ["Surface Temperature", "Heat Uptake", "Ocean Heat Content", "Sea Surface Temperature", "Effective Radiative Forcing"]
+
+
+def config4_builder(axis: TimeAxis | None = None) -> ModelBuilder:
+    """GhgForcing + OzoneForcing + AerosolDirect (FourBox, stored Scalar) + AerosolIndirect -> Sum aggregate ->
+    ClimateUDEB (FourBox Surface Temperature), the schema of the reference's full-forcing regression model
+    (tests/regression/test_ghg_forcing.py:395-464).  The aggregate gets an initial value so that ClimateUDEB's
+    erf_start is defined at the first step."""
+    from .core import GridType
+    from .magicc import AerosolDirectBuilder, AerosolIndirectBuilder, ClimateUDEBBuilder, GhgForcingBuilder, OzoneForcingBuilder
+
+    schema = VariableSchema()
+    for n in ("CO2", "CH4", "N2O"):
+        schema.add_variable(f"Atmospheric Concentration|{n}", "ppm")
+    for n in ("NOx", "CO", "NMVOC", "SOx", "BC", "OC"):
+        schema.add_variable(f"Emissions|{n}", "Mt/yr")
+    schema.add_variable("EESC", "ppt")
+    for n in CONFIG4_ERF_PARTS:
+        schema.add_variable(n, "W/m^2")
+    schema.add_variable("Surface Temperature", "K", GridType.FourBox)
+    for n in ("Heat Uptake", "Ocean Heat Content", "Sea Surface Temperature"):
+        schema.add_variable(n, "")
+    schema.add_aggregate("Effective Radiative Forcing", "W/m^2", "Sum", CONFIG4_ERF_PARTS)
+    return (
+        ModelBuilder().with_time_axis(axis or time_axis()).with_schema(schema)
+        .with_rust_component(GhgForcingBuilder.from_parameters({}).build())
+        .with_rust_component(OzoneForcingBuilder.from_parameters({}).build())
+        .with_rust_component(AerosolDirectBuilder.from_parameters({}).build())
+        .with_rust_component(AerosolIndirectBuilder.from_parameters({}).build())
+        .with_rust_component(ClimateUDEBBuilder.from_parameters({}).build())
+        .with_initial_values({"Surface Temperature": 0.0, "Effective Radiative Forcing": 0.0})
+    )
+
+
+def config4_scenario(years: np.ndarray) -> dict:
+    """Smooth synthetic SSP-like concentration / emission curves."""
+    ramp = np.maximum(0.0, years - 1850.0) / 250.0
+    return {
+        "Atmospheric Concentration|CO2": 278.0 * np.exp(0.0035 * np.maximum(0.0, years - 1850.0)),
+        "Atmospheric Concentration|CH4": 722.0 + 1100.0 * ramp,
+        "Atmospheric Concentration|N2O": 270.0 + 60.0 * ramp,
+        "EESC": 1000.0 + 1500.0 * np.exp(-((years - 2000.0) / 40.0) ** 2),
+        "Emissions|NOx": 10.0 + 30.0 * ramp, "Emissions|CO": 300.0 * ramp, "Emissions|NMVOC": 100.0 * ramp,
+        "Emissions|SOx": 1.0 + 60.0 * ramp * np.exp(-np.maximum(0.0, years - 1990.0) / 60.0),
+        "Emissions|BC": 2.5 + 5.0 * ramp, "Emissions|OC": 10.0 + 20.0 * ramp,
+    }
+
+
+def config4(M: int = 100_000):
+    axis = time_axis()
+    params = uniform_params(CONFIG4_RANGES, M, SEED0 + 3)
+    return config4_builder(axis), CONFIG4_BINDINGS, params, [config4_scenario(axis.values())]

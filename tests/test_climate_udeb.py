@@ -130,3 +130,29 @@ def test_udeb_gpu_parity(dtype, tol, tmp_path, monkeypatch):
     for n in names:
         assert rel_err(got[n], ref[n]) <= tol, n
     assert got["Surface Temperature"].shape == (101, 4, 192)
+
+
+@pytest.mark.gpu
+def test_config4_magicc_boxes_parity_and_fp32(tmp_path, monkeypatch):
+    """BASELINE config 4 graph (forcing boxes -> Sum aggregate -> ClimateUDEB on the four-box grid) at a size the
+    oracle finishes in seconds: fp64 parity 1e-9 on every series; fp32 path measured against the 1e-4 bar."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    b, binds, params, scen = syn.config4(M=160)
+    ens = b.build_ensemble().bind_parameters(binds)
+    sc = ens.pack_scenarios(scen)
+    got = ens.split_outputs(ens.run(params, sc))
+    m = oracle_from_builder(b)
+    names = ens.variable_names
+    ref = m.split(m.run_batch(oracle_bindings(b, binds), params, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
+    st = got["Surface Temperature"]
+    assert st.shape == (351, 4, 160) and np.all(st[0] == 0.0) and np.isfinite(st).all()
+    assert ens.execution_order()[-1] == 4  # ClimateUDEB runs after the ERF aggregator (node 5)
+    # fp32 path
+    e32 = b.build_ensemble(dtype="f32").bind_parameters(binds)
+    g32 = e32.split_outputs(e32.run(params, sc))
+    errs = {n: rel_err(g32[n], ref[n]) for n in syn.CONFIG4_OUTPUTS}
+    print("config4 fp32 relative errors:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["Effective Radiative Forcing"] <= 1e-4
+    assert errs["Surface Temperature"] <= 5e-3  # documented divergence: LAMCALC's 1e-3 tolerance iteration + 50-layer Thomas in fp32

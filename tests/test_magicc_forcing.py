@@ -125,7 +125,9 @@ BINDS = {**syn.TWO_LAYER_BINDINGS, "adjust_ch4": "GhgForcing.adjust_ch4", "sox_c
 
 def _params(M):
     rng = np.random.default_rng(17)
-    return np.column_stack([syn.uniform_params(syn.TWO_LAYER_RANGES, M, 3), rng.uniform(0.7, 1.0, M), rng.uniform(-0.005, -0.002, M),
+    tl = syn.uniform_params(syn.TWO_LAYER_RANGES, M, 3)
+    tl[:, 1] *= 0.2  # keep a*Ts^2 from running away at this forcing level (overflow steps are not comparable)
+    return np.column_stack([tl, rng.uniform(0.7, 1.0, M), rng.uniform(-0.005, -0.002, M),
                             rng.uniform(-1.5, -0.5, M), rng.uniform(0.02, 0.05, M)])
 
 
@@ -147,5 +149,4 @@ def test_full_forcing_graph_parity(aerosol_grid, weights, tmp_path, monkeypatch)
         assert rel_err(got[n], ref[n]) <= 1e-9, n
     direct = got["Effective Radiative Forcing|Aerosol|Direct"]
     assert direct.ndim == (3 if aerosol_grid == GridType.FourBox else 2)
-    # (some members run away through the a*Ts^2 feedback at this forcing level: identically in the oracle)
-    assert np.isfinite(got["Surface Temperature"][:200]).all()
+    assert np.isfinite(got["Surface Temperature"]).all()

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Secondary measurements: the BASELINE.json configs other than the headline one (bench.py covers configs[2]).
+
+  config 2  two-layer ensemble, 1 048 576 members x 1 forcing scenario, fp64 (+ fp32)
+  config 4  MAGICC box components on the four-box grid, 100 000 members, fp64 vs fp32
+  config 5  log-posterior of 1 048 576 two-layer members against 171 synthetic observations (fused K4 kernel)
+
+Each line: device-resident throughput (CUDA events on the launch stream, 3 warm-ups, best of 5), parity of a strided
+subsample against the CPU oracle (fp64 1e-9 / fp32 reported), and the CPU oracle's own throughput on a bounded sample.
+Run on a GPU box:  python tools/bench_configs.py > gpurun_out/configs.jsonl
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import oracle as orc  # noqa: E402  (checker + CPU baseline leg only)
+from rscm_b200 import _ffi, synthetic as syn  # noqa: E402
+from tests.helpers import oracle_bindings, oracle_from_builder, rel_err  # noqa: E402
+
+
+def time_launches(fn, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def run_config(name, builder, binds, params, scen, outputs, dtype, sub_stride, years=350):
+    ens = builder.build_ensemble(dtype=dtype).bind_parameters(binds)
+    ens.select_outputs(outputs)
+    sc_host = ens.pack_scenarios(scen)
+    M, S = params.shape[0], len(scen)
+    d_p = torch.from_numpy(np.ascontiguousarray(params.T)).cuda()
+    d_s = torch.from_numpy(sc_host).cuda()
+    d_o = torch.empty((ens.output_rows, S * M), dtype=torch.float64, device="cuda")
+    ms = time_launches(lambda: ens.run_device(d_p, d_s, d_o, layout=0))
+    torch.cuda.synchronize()
+    idx = np.arange(0, M, sub_stride)
+    sub = d_o[:, torch.from_numpy(np.concatenate([idx + s * M for s in range(S)])).cuda()].cpu().numpy()
+    m = oracle_from_builder(builder)
+    t0 = time.perf_counter()
+    ref = m.run_batch(oracle_bindings(builder, binds), params[idx], ens.exogenous_names, sc_host, outputs)
+    cpu_s = time.perf_counter() - t0
+    got, want = ens.split_outputs(sub), m.split(ref, outputs)
+    errs = {n: rel_err(got[n], want[n]) for n in outputs}
+    line = {"config": name, "dtype": dtype, "members": M, "scenarios": S, "ms": ms, "member_years_per_s": M * S * years / (ms * 1e-3),
+            "jit": ens.program_is_jit(), "parity_subsample": int(idx.size * S), "max_rel_err": max(errs.values()), "rel_err": errs,
+            "cpu_oracle_member_years_per_s": idx.size * S * years / cpu_s, "cpu_threads": orc.max_threads()}
+    print(json.dumps(line), flush=True)
+    return ens
+
+
+def main():
+    # config 2
+    b, binds, params, scen = syn.config2(M=1 << 20)
+    for dt in ("f64", "f32"):
+        run_config("2: two-layer 1M x 1", b, binds, params, scen, ["Surface Temperature", "Deep Ocean Temperature"], dt, 257)
+    # config 4
+    b, binds, params, scen = syn.config4(M=100_000)
+    for dt in ("f64", "f32"):
+        run_config("4: MAGICC boxes + ClimateUDEB (four-box) 100k", b, binds, params, scen, syn.CONFIG4_OUTPUTS, dt, 499)
+    # config 5: fused log-posterior
+    b, binds, params, scen = syn.config2(M=1 << 20)
+    ens = b.build_ensemble().bind_parameters(binds)
+    sc_host = ens.pack_scenarios(scen)
+    truth = dict(syn.TWO_LAYER_DEFAULTS, lambda0=1.1, efficacy=1.3, a=0.05)
+    ens.select_outputs(["Surface Temperature"])
+    t_true = ens.run(np.array([[truth[k] for k in syn.TWO_LAYER_RANGES]]), sc_host)[:, 0]
+    obs = syn.config5_observations(t_true, syn.time_axis().values())
+    priors = [(_ffi.PRIOR_UNIFORM, lo, hi) for lo, hi in syn.TWO_LAYER_RANGES.values()]
+    ens.set_target(obs).set_priors(priors)
+    M = params.shape[0]
+    d_p = torch.from_numpy(np.ascontiguousarray(params.T)).cuda()
+    d_s = torch.from_numpy(sc_host).cuda()
+    d_lp = torch.empty(M, dtype=torch.float64, device="cuda")
+    d_sum = torch.zeros(5, dtype=torch.float64, device="cuda")
+    ms = time_launches(lambda: ens.log_posterior_device(d_p, d_s, d_lp, d_sum, layout=0))
+    idx = np.arange(0, M, 257)
+    m = oracle_from_builder(b)
+    t0 = time.perf_counter()
+    ref = m.log_posterior_batch(oracle_bindings(b, binds), params[idx], ens.exogenous_names, sc_host, priors, obs)
+    cpu_s = time.perf_counter() - t0
+    got = d_lp.cpu().numpy()[idx]
+    fin = np.isfinite(ref)
+    err = float(np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])))
+    print(json.dumps({"config": "5: log-posterior, 1M two-layer members, 171 observations", "dtype": "f64", "members": M, "ms": ms,
+                      "member_years_per_s": M * 350 / (ms * 1e-3), "bytes_out_per_member": 8, "max_rel_err": err,
+                      "inf_match": bool(np.array_equal(np.isinf(got), np.isinf(ref))),
+                      "cpu_oracle_member_years_per_s": idx.size * 350 / cpu_s, "cpu_threads": orc.max_threads()}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
