@@ -54,7 +54,13 @@ typedef enum {
     RSCM_B200_OZONE_FORCING = 6,    /* crates/rscm-magicc/src/parameters/ozone_forcing.rs */
     RSCM_B200_AEROSOL_DIRECT = 7,   /* crates/rscm-magicc/src/parameters/aerosol.rs (AerosolDirectParameters) */
     RSCM_B200_AEROSOL_INDIRECT = 8, /* crates/rscm-magicc/src/parameters/aerosol.rs (AerosolIndirectParameters) */
-    RSCM_B200_CLIMATE_UDEB = 9      /* crates/rscm-magicc/src/parameters/climate_udeb.rs */
+    RSCM_B200_CLIMATE_UDEB = 9,     /* crates/rscm-magicc/src/parameters/climate_udeb.rs */
+    RSCM_B200_FOUR_BOX_OHU = 10,    /* crates/rscm-components/src/components/four_box_ocean_heat_uptake.rs */
+    RSCM_B200_OCEAN_SURFACE_PP = 11, /* .../ocean_carbon_cycle/ocean_surface_partial_pressure.rs */
+    RSCM_B200_CO2_BUDGET = 12,      /* crates/rscm-magicc/src/parameters/co2_budget.rs */
+    RSCM_B200_TERRESTRIAL_CARBON = 13, /* crates/rscm-magicc/src/parameters/terrestrial_carbon.rs */
+    RSCM_B200_CH4_CHEMISTRY = 14,   /* crates/rscm-magicc/src/parameters/ch4_chemistry.rs */
+    RSCM_B200_N2O_CHEMISTRY = 15    /* crates/rscm-magicc/src/parameters/n2o_chemistry.rs */
 } rscm_b200_component_kind;
 
 /* GridType — crates/rscm-core/src/component.rs:56-64 */
@@ -82,6 +88,9 @@ typedef enum { RSCM_B200_SRC_EXOGENOUS = 0, RSCM_B200_SRC_OWN_STATE = 1, RSCM_B2
  *                  oc_pi, harmonize, harmonize_year, harmonize_target
  *   CLIMATE_UDEB : the fields of ClimateUDEBParameters in declaration order (rf_regions_co2
  *                  expanded to 4 values, booleans/enums as 0/1/2), see rscm_b200/magicc.py
+ *   FOUR_BOX_OHU, OCEAN_SURFACE_PP, CO2_BUDGET, TERRESTRIAL_CARBON, CH4_CHEMISTRY, N2O_CHEMISTRY:
+ *                  the fields of the reference's parameter struct in declaration order, arrays
+ *                  expanded, booleans as 0/1 (rscm_b200/components.py, rscm_b200/magicc.py)
  */
 typedef struct {
     int32_t kind;     /* rscm_b200_component_kind */

@@ -332,6 +332,12 @@ const orc_kind_info *orc_kind_lookup(int kind)
     case ORC_AEROSOL_DIRECT: return &orc_kind_aerosol_direct;
     case ORC_AEROSOL_INDIRECT: return &orc_kind_aerosol_indirect;
     case ORC_CLIMATE_UDEB: return &orc_kind_climate_udeb;
+    case ORC_FOUR_BOX_OHU: return &orc_kind_fbohu;
+    case ORC_OCEAN_SURFACE_PP: return &orc_kind_ospp;
+    case ORC_CO2_BUDGET: return &orc_kind_co2_budget;
+    case ORC_TERRESTRIAL_CARBON: return &orc_kind_terrestrial;
+    case ORC_CH4_CHEMISTRY: return &orc_kind_ch4;
+    case ORC_N2O_CHEMISTRY: return &orc_kind_n2o;
     default: return NULL;
     }
 }

@@ -59,6 +59,12 @@ enum {
     ORC_AEROSOL_DIRECT = 7,
     ORC_AEROSOL_INDIRECT = 8,
     ORC_CLIMATE_UDEB = 9,  /* params: see magicc_climate.c */
+    ORC_FOUR_BOX_OHU = 10, /* the following: see magicc_boxes.c */
+    ORC_OCEAN_SURFACE_PP = 11,
+    ORC_CO2_BUDGET = 12,
+    ORC_TERRESTRIAL_CARBON = 13,
+    ORC_CH4_CHEMISTRY = 14,
+    ORC_N2O_CHEMISTRY = 15,
     ORC_KIND_MAX = 32
 };
 

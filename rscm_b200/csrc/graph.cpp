@@ -155,6 +155,66 @@ static const std::vector<KindInfo> &kinds()
          {0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 1},
          96, /*n_state*/ 19, /*n_smem*/ 150, /*scratch_per_T*/ 1, /*needs_time*/ true,
          /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table},
+        {RSCM_B200_FOUR_BOX_OHU, "FourBoxOceanHeatUptake", "four_box_ohu",
+         // crates/rscm-components/src/components/four_box_ocean_heat_uptake.rs
+         {{"Effective Radiative Forcing|Aggregated", REQ_INPUT, RSCM_B200_SCALAR}, {"Heat Uptake|Ocean", REQ_OUTPUT, RSCM_B200_FOUR_BOX}},
+         {"northern_ocean_ratio", "northern_land_ratio", "southern_ocean_ratio", "southern_land_ratio"},
+         1, -2, {1, 1, 1, 1}, 4},
+        {RSCM_B200_OCEAN_SURFACE_PP, "OceanSurfacePartialPressure", "ocean_surface_pp",
+         // crates/rscm-components/src/components/ocean_carbon_cycle/ocean_surface_partial_pressure.rs
+         {{"Sea Surface Temperature", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Dissolved Inorganic Carbon", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Ocean Surface Partial Pressure|CO2", REQ_OUTPUT, RSCM_B200_SCALAR}},
+         {"ospp_preindustrial", "sensitivity_ospp_to_temperature", "sea_surface_temperature_preindustrial", "delta_ospp_offsets_0",
+          "delta_ospp_offsets_1", "delta_ospp_offsets_2", "delta_ospp_offsets_3", "delta_ospp_offsets_4", "delta_ospp_coefficients_0",
+          "delta_ospp_coefficients_1", "delta_ospp_coefficients_2", "delta_ospp_coefficients_3", "delta_ospp_coefficients_4"},
+         1, -2, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 8},
+        {RSCM_B200_CO2_BUDGET, "CO2Budget", "co2_budget",
+         // crates/rscm-magicc/src/carbon/budget.rs (derive block)
+         {{"Emissions|CO2|Fossil", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|CO2|Land Use", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Carbon Flux|Terrestrial", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Carbon Flux|Ocean", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|CO2|Net", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Airborne Fraction|CO2", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Atmospheric Concentration|CO2", REQ_STATE, RSCM_B200_SCALAR}},
+         {"gtc_per_ppm", "co2_pi"},
+         1, -2, {1, 1}, 4, 0, 0, 0, /*needs_time*/ true},
+        {RSCM_B200_TERRESTRIAL_CARBON, "TerrestrialCarbon", "terrestrial_carbon",
+         // crates/rscm-magicc/src/carbon/terrestrial.rs (derive block)
+         {{"Atmospheric Concentration|CO2", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Surface Temperature", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|CO2|Land Use", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Carbon Flux|Terrestrial", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Carbon Pool|Plant", REQ_STATE, RSCM_B200_SCALAR},
+          {"Carbon Pool|Detritus", REQ_STATE, RSCM_B200_SCALAR},
+          {"Carbon Pool|Soil", REQ_STATE, RSCM_B200_SCALAR},
+          {"Carbon Pool|Humus", REQ_STATE, RSCM_B200_SCALAR}},
+         {"npp_pi", "co2_pi", "beta", "npp_temp_sensitivity", "resp_temp_sensitivity", "detritus_temp_sensitivity", "soil_temp_sensitivity",
+          "humus_temp_sensitivity", "plant_pool_pi", "detritus_pool_pi", "soil_pool_pi", "humus_pool_pi", "respiration_pi",
+          "frac_npp_to_plant", "frac_npp_to_detritus", "frac_plant_to_detritus", "frac_detritus_to_soil", "frac_soil_to_humus",
+          "enable_fertilization", "enable_temp_feedback"},
+         5, -2, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0}, 24, 0, 0, 0, /*needs_time*/ true},
+        {RSCM_B200_CH4_CHEMISTRY, "CH4Chemistry", "ch4_chemistry",
+         // crates/rscm-magicc/src/chemistry/ch4.rs (derive block)
+         {{"Emissions|CH4", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Surface Temperature", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|NOx", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|CO", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Emissions|NMVOC", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Lifetime|CH4", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Atmospheric Concentration|CH4", REQ_STATE, RSCM_B200_SCALAR}},
+         {"ch4_pi", "natural_emissions", "tau_oh", "tau_soil", "tau_strat", "tau_trop_cl", "ch4_self_feedback", "oh_sensitivity_scale",
+          "oh_nox_sensitivity", "oh_co_sensitivity", "oh_nmvoc_sensitivity", "temp_sensitivity", "include_temp_feedback",
+          "include_emissions_feedback", "ppb_to_tg", "nox_reference", "co_reference", "nmvoc_reference"},
+         1, -2, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 1, 1, 1, 1}, 24, /*n_state*/ 1},
+        {RSCM_B200_N2O_CHEMISTRY, "N2OChemistry", "n2o_chemistry",
+         // crates/rscm-magicc/src/chemistry/n2o.rs (derive block)
+         {{"Emissions|N2O", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Lifetime|N2O", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Atmospheric Concentration|N2O", REQ_STATE, RSCM_B200_SCALAR}},
+         {"n2o_pi", "natural_emissions", "tau_n2o", "lifetime_feedback", "strat_delay", "ppb_to_tg"},
+         1, -2, {1, 1, 1, 1, 0, 1}, 16, /*n_state*/ 8, 0, 0, /*needs_time*/ true},
     };
     return k;
 }
@@ -644,6 +704,10 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
             const std::vector<double> tab = k->const_table(n.params, terr);
             if (!terr.empty()) { err = terr; return false; }
             g.ctab.insert(g.ctab.end(), tab.begin(), tab.end());
+        }
+        if (n.kind == RSCM_B200_N2O_CHEMISTRY && !(n.params[4] >= 0.0 && n.params[4] <= 6.0)) {
+            err = "N2OChemistry: strat_delay must be in [0, 6] (history ring of the device kernel)";
+            return false;
         }
         if (n.kind == RSCM_B200_CLIMATE_UDEB && n.params[34] != 2.0) {
             // analytical initial profile depends on kappa and w_initial: they feed the host-computed table

@@ -19,6 +19,7 @@
 // (no standard headers: this file is also compiled by NVRTC at run time)
 #include "components.cuh"
 #include "climate_udeb.cuh"
+#include "magicc_boxes.cuh"
 #define RSCM_INF (__longlong_as_double(0x7ff0000000000000LL))
 
 namespace rscm_dev {

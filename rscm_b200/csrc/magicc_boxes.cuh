@@ -1,0 +1,182 @@
+// magicc_boxes.cuh — scalar box components on the device (one call = one member, one time step, registers only).
+//
+// Reference: crates/rscm-components/src/components/four_box_ocean_heat_uptake.rs,
+// .../ocean_carbon_cycle/ocean_surface_partial_pressure.rs, crates/rscm-magicc/src/carbon/budget.rs:121-205,
+// carbon/terrestrial.rs:213-343 (+ parameters/terrestrial_carbon.rs turnover times), chemistry/ch4.rs:55-350,
+// chemistry/n2o.rs:171-275.  History-dependent accessors (`previous()`, `at_offset(-k)`) are served from a short
+// per-thread ring of the component's own state (S[]), refreshed at the end of every solve.
+#pragma once
+
+namespace rscm_dev {
+
+// ---- FourBoxOceanHeatUptake: P = 4 regional ratios; in: ERF|Aggregated; out: FourBox heat uptake ----
+template <class R> __device__ __forceinline__ void four_box_ohu_prepare(const R *, R *D) { D[0] = R(0); }
+template <class R>
+__device__ __forceinline__ bool four_box_ohu_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = in[0] * P[i];
+    return true;
+}
+
+// ---- OceanSurfacePartialPressure: P = ospp_pi, sensitivity, sst_pi, offsets[5], coefficients[5] ----
+template <class R> __device__ __forceinline__ void ocean_surface_pp_prepare(const R *, R *D) { D[0] = R(0); }
+template <class R>
+__device__ __forceinline__ bool ocean_surface_pp_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
+{
+    const R d = in[1];
+    const R d2 = d * d, d3 = d2 * d, d4 = d2 * d2;
+    const R bits[5] = {d, d2 * R(10e-3), -d3 * R(10e-5), d4 * R(10e-7), -d4 * R(10e-10)};
+    R dot = R(0);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dot += (P[3 + i] + P[8 + i] * P[2]) * bits[i];
+    out[0] = (P[0] + dot) * r_exp<R>(P[1] * in[0]);
+    return true;
+}
+
+// ---- CO2Budget: P = gtc_per_ppm, co2_pi; in: fossil, landuse, terrestrial flux, ocean flux, CO2 (state) ----
+template <class R> __device__ __forceinline__ void co2_budget_prepare(const R *, R *D) { D[0] = R(0); }
+template <class R>
+__device__ __forceinline__ bool co2_budget_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &cx, R *, NodeRef)
+{
+    const R dt = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
+    const R total_emissions = in[0] + in[1];
+    const R net = total_emissions - (in[2] + in[3]);
+    out[0] = net;
+    out[1] = (total_emissions > R(0)) ? net / total_emissions : R(0);
+    out[2] = in[4] + (net * dt) / P[0];
+    return true;
+}
+
+// ---- TerrestrialCarbon: 4 pools, implicit trapezoid; D = turnover times (plant, detritus, soil, humus), frac_npp_to_soil ----
+template <class R> __device__ __forceinline__ void terrestrial_carbon_prepare(const R *P, R *D)
+{
+    const R frac_npp_to_soil = r_max(R(1) - P[13] - P[14], R(0));
+    const R net_flux_plant = P[13] * P[0] - P[12];
+    const R tau_plant = (net_flux_plant > R(1e-10)) ? P[8] / net_flux_plant : R(100);
+    const R flux_into_det = P[14] * P[0] + P[15] * net_flux_plant;
+    const R tau_det = (flux_into_det > R(1e-10)) ? P[9] / flux_into_det : R(3);
+    const R flux_det_out = P[9] / tau_det;
+    const R flux_into_soil = frac_npp_to_soil * P[0] + (R(1) - P[15]) * net_flux_plant + P[16] * flux_det_out;
+    const R tau_soil = (flux_into_soil > R(1e-10)) ? P[10] / flux_into_soil : R(50);
+    const R flux_soil_out = P[10] / tau_soil;
+    const R flux_into_hum = P[17] * flux_soil_out;
+    const R tau_hum = (flux_into_hum > R(1e-10)) ? P[11] / flux_into_hum : R(1000);
+    D[0] = tau_plant; D[1] = tau_det; D[2] = tau_soil; D[3] = tau_hum; D[4] = frac_npp_to_soil;
+}
+
+template <class R> __device__ __forceinline__ void tc_pool_step(R pool, R tau, R flux_in, R temp_factor, R dt, R &new_pool, R &turnover)
+{
+    const R k_eff = temp_factor / tau;
+    const R half_k = R(0.5) * k_eff * dt;
+    new_pool = r_max(((R(1) - half_k) * pool + flux_in * dt) / (R(1) + half_k), R(0));
+    turnover = R(0.5) * k_eff * (pool + new_pool);
+}
+
+template <class R>
+__device__ __forceinline__ bool terrestrial_carbon_solve(const R *P, const R *D, const R *in, R *out, const StepCtx<R> &cx, R *, NodeRef)
+{
+    const R co2 = in[0], temperature = in[1], landuse = in[2];
+    const R dt = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
+    R fert = R(1);
+    if (P[18] != R(0) && !(co2 <= R(0))) fert = r_max(R(1) + P[2] * r_log<R>(co2 / P[1]), R(0.1));
+    const bool tf = P[19] != R(0);
+    const R npp = P[0] * fert * (tf ? r_exp<R>(P[3] * temperature) : R(1));
+    const R respiration = P[12] * fert * (tf ? r_exp<R>(P[4] * temperature) : R(1));
+    const R tf_det = tf ? r_exp<R>(P[5] * temperature) : R(1);
+    const R tf_soil = tf ? r_exp<R>(P[6] * temperature) : R(1);
+    const R tf_hum = tf ? r_exp<R>(P[7] * temperature) : R(1);
+    R new_plant, to_plant, new_det, to_det, new_soil, to_soil, new_hum, to_hum;
+    tc_pool_step<R>(in[3], D[0], npp * P[13] - respiration - landuse, R(1), dt, new_plant, to_plant);
+    tc_pool_step<R>(in[4], D[1], npp * P[14] + P[15] * to_plant, tf_det, dt, new_det, to_det);
+    tc_pool_step<R>(in[5], D[2], npp * D[4] + (R(1) - P[15]) * to_plant + P[16] * to_det, tf_soil, dt, new_soil, to_soil);
+    tc_pool_step<R>(in[6], D[3], P[17] * to_soil, tf_hum, dt, new_hum, to_hum);
+    const R total_resp = respiration + (R(1) - P[16]) * to_det + (R(1) - P[17]) * to_soil + to_hum;
+    out[0] = npp - total_resp - landuse;
+    out[1] = new_plant; out[2] = new_det; out[3] = new_soil; out[4] = new_hum;
+    return true;
+}
+
+// ---- CH4Chemistry: 4 Prather iterations; S[0] = CH4 at index N-1 (previous()) ----
+template <class R> __device__ __forceinline__ void ch4_chemistry_prepare(const R *P, R *D)
+{
+    D[0] = R(1) / (R(1) / P[3] + R(1) / P[4] + R(1) / P[5]); // tau_other
+}
+template <class R> __device__ __forceinline__ void ch4_chemistry_init_state(const R *, const R *, R *S, const StepCtx<R> &, NodeRef) { S[0] = R(0); }
+
+template <class R>
+__device__ __forceinline__ bool ch4_chemistry_solve(const R *P, const R *D, const R *in, R *out, const StepCtx<R> &cx, R *S, NodeRef)
+{
+    const R ch4_current = in[5];
+    const R ch4_prev = (cx.N > 0) ? S[0] : ch4_current;
+    S[0] = ch4_current;
+    const R emissions = in[0], temperature = in[1];
+    const R total_emissions = emissions + P[1];
+    const R burden_prev = ch4_prev * P[14], burden_ref = P[0] * P[14];
+    const R tau_other = D[0];
+    R base = P[2];
+    if (P[13] != R(0))
+        base = P[2] * r_exp<R>(-P[7] * (P[8] * (in[2] - P[15]) + P[9] * (in[3] - P[16]) + P[10] * (in[4] - P[17])));
+    const R x = -P[7] * P[6];
+    R burden = ch4_current * P[14], delta_burden = R(0), tau_oh = P[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const R burden_mean = (burden + burden_prev) / R(2);
+        R tau = base * r_pow<R>(r_max(burden_mean / burden_ref, R(1)), x);
+        if (i > 0 && !(r_abs(burden_prev) < R(1e-10))) tau = tau * (R(1) - R(0.5) * x * delta_burden / burden_prev);
+        if (P[12] != R(0) && !(r_abs(temperature) < R(1e-10))) tau = P[2] / (P[2] / tau + P[11] * r_max(temperature, R(0)));
+        delta_burden = total_emissions - burden_mean / tau - burden_mean / tau_other;
+        burden = burden_prev + delta_burden;
+        tau_oh = tau;
+    }
+    out[0] = R(1) / (R(1) / tau_oh + R(1) / tau_other);
+    out[1] = burden / P[14];
+    return true;
+}
+
+// ---- N2OChemistry: S[j] = N2O at index N-1-j, j < 8 (previous(), at_offset(-delay), at_offset(-delay-1)) ----
+constexpr int N2O_RING = 8;
+template <class R> __device__ __forceinline__ void n2o_chemistry_prepare(const R *, R *D) { D[0] = R(0); }
+template <class R> __device__ __forceinline__ void n2o_chemistry_init_state(const R *, const R *, R *S, const StepCtx<R> &, NodeRef)
+{
+#pragma unroll
+    for (int j = 0; j < N2O_RING; ++j) S[j] = R(0);
+}
+
+template <class R>
+__device__ __forceinline__ bool n2o_chemistry_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &cx, R *S, NodeRef)
+{
+    const R dt = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
+    const R cur = in[1];
+    const int N = cx.N;
+    auto back = [&](int k, R fallback) -> R { // value at index N-k (k >= 1) or the fallback when out of range
+        R v = fallback;
+#pragma unroll
+        for (int j = 0; j < N2O_RING; ++j)
+            if (j == k - 1 && N - k >= 0) v = S[j];
+        return v;
+    };
+    const R prev = back(1, cur);
+    int delay = static_cast<int>(P[4]);
+    if (delay < 1) delay = 1;
+    const R t_delay = back(delay, prev);
+    const R t_delay_m1 = back(delay + 1, t_delay);
+    const R lagged = (t_delay + t_delay_m1) / R(2);
+#pragma unroll
+    for (int j = N2O_RING - 1; j > 0; --j) S[j] = S[j - 1];
+    S[0] = cur;
+    const R total_emissions = in[0] + P[1];
+    const R burden_prev = prev * P[5], burden_lagged = lagged * P[5], burden_ref = P[0] * P[5];
+    R burden = cur * P[5], tau_eff = P[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const R mid = (burden_prev + burden) / R(2);
+        tau_eff = P[2] * r_pow<R>(r_max(mid / burden_ref, R(1)), P[3]);
+        burden = burden_prev + (total_emissions - burden_lagged / tau_eff) * dt;
+    }
+    out[0] = tau_eff;
+    out[1] = burden / P[5];
+    return true;
+}
+
+} // namespace rscm_dev

@@ -8,7 +8,8 @@ from . import _ffi
 from ._builders import ComponentBuilder
 from .core import Component
 
-__all__ = ["GhgForcingBuilder", "OzoneForcingBuilder", "AerosolDirectBuilder", "AerosolIndirectBuilder", "ClimateUDEBBuilder"]
+__all__ = ["GhgForcingBuilder", "OzoneForcingBuilder", "AerosolDirectBuilder", "AerosolIndirectBuilder", "ClimateUDEBBuilder",
+           "CO2BudgetBuilder", "TerrestrialCarbonBuilder", "CH4ChemistryBuilder", "N2OChemistryBuilder"]
 
 
 class GhgForcingBuilder(ComponentBuilder):
@@ -109,6 +110,50 @@ class AerosolIndirectBuilder(ComponentBuilder):
         ("cloud_albedo_coefficient", -1.0), ("reference_burden", 50.0), ("sox_weight", 1.0), ("oc_weight", 0.3),
         ("sox_pi", 1.0), ("oc_pi", 10.0), ("harmonize", 0.0), ("harmonize_year", 2019.0), ("harmonize_target", -0.89),
     )
+
+
+class CO2BudgetBuilder(ComponentBuilder):
+    """CO2BudgetParameters — crates/rscm-magicc/src/parameters/co2_budget.rs:35-42."""
+
+    KIND = _ffi.CO2_BUDGET
+    TYPE_NAME = "CO2Budget"
+    FIELDS = (("gtc_per_ppm", 2.123), ("co2_pi", 278.0))
+
+
+class TerrestrialCarbonBuilder(ComponentBuilder):
+    """TerrestrialCarbonParameters — crates/rscm-magicc/src/parameters/terrestrial_carbon.rs:153-190."""
+
+    KIND = _ffi.TERRESTRIAL_CARBON
+    TYPE_NAME = "TerrestrialCarbon"
+    FIELDS = (
+        ("npp_pi", 66.27), ("co2_pi", 278.0), ("beta", 0.6486), ("npp_temp_sensitivity", 0.0107), ("resp_temp_sensitivity", 0.0685),
+        ("detritus_temp_sensitivity", 0.1358), ("soil_temp_sensitivity", 0.1541), ("humus_temp_sensitivity", 0.05),
+        ("plant_pool_pi", 884.86), ("detritus_pool_pi", 92.77), ("soil_pool_pi", 1681.53), ("humus_pool_pi", 836.0),
+        ("respiration_pi", 12.26), ("frac_npp_to_plant", 0.4483), ("frac_npp_to_detritus", 0.3998), ("frac_plant_to_detritus", 0.9989),
+        ("frac_detritus_to_soil", 0.3), ("frac_soil_to_humus", 0.1), ("enable_fertilization", 1.0), ("enable_temp_feedback", 1.0),
+    )
+
+
+class CH4ChemistryBuilder(ComponentBuilder):
+    """CH4ChemistryParameters — crates/rscm-magicc/src/parameters/ch4_chemistry.rs:131-152."""
+
+    KIND = _ffi.CH4_CHEMISTRY
+    TYPE_NAME = "CH4Chemistry"
+    FIELDS = (
+        ("ch4_pi", 722.0), ("natural_emissions", 209.0), ("tau_oh", 9.3), ("tau_soil", 150.0), ("tau_strat", 120.0), ("tau_trop_cl", 200.0),
+        ("ch4_self_feedback", -0.32), ("oh_sensitivity_scale", 0.72), ("oh_nox_sensitivity", 0.0042), ("oh_co_sensitivity", -0.000105),
+        ("oh_nmvoc_sensitivity", -0.000315), ("temp_sensitivity", 0.0316), ("include_temp_feedback", 1.0),
+        ("include_emissions_feedback", 1.0), ("ppb_to_tg", 2.75), ("nox_reference", 0.0), ("co_reference", 0.0), ("nmvoc_reference", 0.0),
+    )
+
+
+class N2OChemistryBuilder(ComponentBuilder):
+    """N2OChemistryParameters — crates/rscm-magicc/src/parameters/n2o_chemistry.rs:78-88."""
+
+    KIND = _ffi.N2O_CHEMISTRY
+    TYPE_NAME = "N2OChemistry"
+    FIELDS = (("n2o_pi", 270.0), ("natural_emissions", 11.0), ("tau_n2o", 139.275), ("lifetime_feedback", -0.04), ("strat_delay", 1),
+              ("ppb_to_tg", 4.79))
 
 
 class ClimateUDEBBuilder(_ArrayFieldsBuilder):
