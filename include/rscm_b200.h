@@ -60,7 +60,8 @@ typedef enum {
     RSCM_B200_CO2_BUDGET = 12,      /* crates/rscm-magicc/src/parameters/co2_budget.rs */
     RSCM_B200_TERRESTRIAL_CARBON = 13, /* crates/rscm-magicc/src/parameters/terrestrial_carbon.rs */
     RSCM_B200_CH4_CHEMISTRY = 14,   /* crates/rscm-magicc/src/parameters/ch4_chemistry.rs */
-    RSCM_B200_N2O_CHEMISTRY = 15    /* crates/rscm-magicc/src/parameters/n2o_chemistry.rs */
+    RSCM_B200_N2O_CHEMISTRY = 15,   /* crates/rscm-magicc/src/parameters/n2o_chemistry.rs */
+    RSCM_B200_OCEAN_CARBON = 16     /* crates/rscm-magicc/src/parameters/ocean_carbon.rs (IRF forms flattened, 60 values) */
 } rscm_b200_component_kind;
 
 /* GridType — crates/rscm-core/src/component.rs:56-64 */

@@ -140,5 +140,6 @@ extern const orc_kind_info orc_kind_aerosol_direct;
 extern const orc_kind_info orc_kind_aerosol_indirect;
 extern const orc_kind_info orc_kind_climate_udeb;
 extern const orc_kind_info orc_kind_fbohu, orc_kind_ospp, orc_kind_co2_budget, orc_kind_terrestrial, orc_kind_ch4, orc_kind_n2o;
+extern const orc_kind_info orc_kind_ocean_carbon;
 
 #endif

@@ -65,6 +65,7 @@ enum {
     ORC_TERRESTRIAL_CARBON = 13,
     ORC_CH4_CHEMISTRY = 14,
     ORC_N2O_CHEMISTRY = 15,
+    ORC_OCEAN_CARBON = 16, /* see magicc_ocean.c */
     ORC_KIND_MAX = 32
 };
 

@@ -25,6 +25,7 @@ template <class R> struct StepCtx {
     const int *nsub;      // RK4 sub-step tables [n_rk][Tpad] (shared memory)
     const double *bounds; // time bounds (shared memory; valid when Prog::NEEDS_TIME)
     const double *ctab;   // per-graph constant tables (shared memory)
+    const double *gtab;   // large per-graph constant tables (global memory, read through the read-only path)
     R *sm;                // this thread's shared-memory scratch: element j at sm[j * BLOCK]
     double *scratch;      // this run's global scratch: element j at scratch[j * runs]
     long long runs;
@@ -32,9 +33,10 @@ template <class R> struct StepCtx {
     int N;                // current time index
 };
 
-// Per-node literals the emitter passes: RK4 table row, offsets into ctab / sm / scratch.
+// Per-node literals the emitter passes: RK4 table row, offsets into ctab / sm / scratch / gtab, and one
+// kind-specific integer (e.g. OceanCarbon's steps_per_year) that must be a compile-time constant.
 struct NodeRef {
-    int rk, ctab, sm, scr;
+    int rk, ctab, sm, scr, gt, aux;
 };
 
 template <class R> __device__ __forceinline__ R r_exp(R x);

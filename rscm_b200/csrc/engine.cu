@@ -93,7 +93,7 @@ struct rscm_b200_ensemble {
     double *d_exo = nullptr;
     int64_t exo_capacity_S = 0;
     int *d_nsub = nullptr;
-    double *d_bounds = nullptr, *d_ctab = nullptr;
+    double *d_bounds = nullptr, *d_ctab = nullptr, *d_gtab = nullptr;
     double *d_scratch[2] = {nullptr, nullptr};
     int64_t cap_scratch[2] = {0, 0};
     double *d_obs = nullptr;
@@ -222,6 +222,7 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     a.nsub = h->d_nsub;
     a.bounds = h->d_bounds;
     a.ctab = h->d_ctab;
+    a.gtab = h->d_gtab;
     a.n_ctab = static_cast<int>(g.ctab.size());
     if (g.n_scratch_rows > 0) {
         // global scratch of stateful components, one buffer per launch stream slot
@@ -415,6 +416,10 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
         cudaMalloc(&h->d_ctab, g.ctab.size() * 8);
         cudaMemcpy(h->d_ctab, g.ctab.data(), g.ctab.size() * 8, cudaMemcpyHostToDevice);
     }
+    if (!g.gtab.empty()) {
+        cudaMalloc(&h->d_gtab, g.gtab.size() * 8);
+        cudaMemcpy(h->d_gtab, g.gtab.data(), g.gtab.size() * 8, cudaMemcpyHostToDevice);
+    }
     // scenario row map: user layout [S][exo var][T][R] -> staged rows
     if (g.n_exo_rows > 0) {
         std::vector<int> off(g.n_exo_rows), stride(g.n_exo_rows);
@@ -449,7 +454,7 @@ void rscm_b200_ensemble_destroy(rscm_b200_ensemble *h)
 {
     if (!h) return;
     cudaFree(h->d_exo); cudaFree(h->d_nsub); cudaFree(h->d_obs); cudaFree(h->d_priors); cudaFree(h->d_partials);
-    cudaFree(h->d_bounds); cudaFree(h->d_ctab); cudaFree(h->d_scratch[0]); cudaFree(h->d_scratch[1]);
+    cudaFree(h->d_bounds); cudaFree(h->d_ctab); cudaFree(h->d_gtab); cudaFree(h->d_scratch[0]); cudaFree(h->d_scratch[1]);
     cudaFree(h->d_ticket); cudaFree(h->d_row_off); cudaFree(h->d_row_stride); cudaFree(h->d_scen);
     cudaFree(h->d_logpost); cudaFree(h->d_summary);
     for (int i = 0; i < 2; ++i) {

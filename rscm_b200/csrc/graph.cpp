@@ -63,6 +63,38 @@ static std::vector<double> udeb_const_table(const std::vector<double> &p, std::s
     return t;
 }
 
+// OceanCarbon: scaled impulse-response function by lag in months, irf(k/12) for k = 0 .. steps*(T-1)
+// (OceanCarbonParameters::irf / scale_irf, IrfForm::evaluate — crates/rscm-magicc/src/parameters/ocean_carbon.rs:99-130,378-397)
+static std::vector<double> ocean_irf_table(const std::vector<double> &p, int n_times, std::string &err)
+{
+    const int steps = static_cast<int>(p[10]);
+    if (steps < 1 || steps > 16 || p[10] != steps) { err = "OceanCarbon: steps_per_year must be an integer in [1, 16]"; return {}; }
+    const long long months = static_cast<long long>(steps) * (n_times - 1);
+    if (months > static_cast<long long>(p[11])) {
+        err = "OceanCarbon: run length exceeds max_history_months (history truncation is not implemented on the device)";
+        return {};
+    }
+    auto form = [](const double *f, double t) {
+        const int n = static_cast<int>(f[1]);
+        if (f[0] == 0.0) {
+            double r = 0.0;
+            for (int i = n - 1; i >= 0; --i) r = r * t + f[2 + i];
+            return r;
+        }
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += f[2 + i] * std::exp(-t / f[10 + i]);
+        return s;
+    };
+    if (p[14] < 1 || p[14] > 8 || p[32] < 1 || p[32] > 8) { err = "OceanCarbon: IRF forms take 1..8 terms"; return {}; }
+    std::vector<double> tab(static_cast<size_t>(months) + 2);
+    for (size_t k = 0; k < tab.size(); ++k) {
+        const double t = static_cast<double>(k) * (1.0 / 12.0);
+        const double raw = (t < p[12]) ? form(&p[13], t) : form(&p[31], t);
+        tab[k] = (raw * p[6]) / (raw * p[6] + 1.0 - raw);
+    }
+    return tab;
+}
+
 static const std::vector<KindInfo> &kinds()
 {
     static const std::vector<KindInfo> k = {
@@ -215,6 +247,30 @@ static const std::vector<KindInfo> &kinds()
           {"Atmospheric Concentration|N2O", REQ_STATE, RSCM_B200_SCALAR}},
          {"n2o_pi", "natural_emissions", "tau_n2o", "lifetime_feedback", "strat_delay", "ppb_to_tg"},
          1, -2, {1, 1, 1, 1, 0, 1}, 16, /*n_state*/ 8, 0, 0, /*needs_time*/ true},
+        {RSCM_B200_OCEAN_CARBON, "OceanCarbon", "ocean_carbon",
+         // crates/rscm-magicc/src/carbon/ocean.rs (derive block)
+         {{"Atmospheric Concentration|CO2", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Sea Surface Temperature", REQ_INPUT, RSCM_B200_SCALAR},
+          {"Carbon Flux|Ocean", REQ_OUTPUT, RSCM_B200_SCALAR},
+          {"Ocean Surface pCO2", REQ_STATE, RSCM_B200_SCALAR},
+          {"Cumulative Ocean Uptake", REQ_STATE, RSCM_B200_SCALAR}},
+         {"model", "co2_pi", "pco2_pi", "gas_exchange_scale", "gas_exchange_tau", "temp_sensitivity", "irf_scale", "mixed_layer_depth",
+          "ocean_surface_area", "sst_pi", "steps_per_year", "max_history_months", "irf_switch_time",
+          "irf_early_kind", "irf_early_n", "irf_early_c0", "irf_early_c1", "irf_early_c2", "irf_early_c3", "irf_early_c4", "irf_early_c5",
+          "irf_early_c6", "irf_early_c7", "irf_early_t0", "irf_early_t1", "irf_early_t2", "irf_early_t3", "irf_early_t4", "irf_early_t5",
+          "irf_early_t6", "irf_early_t7",
+          "irf_late_kind", "irf_late_n", "irf_late_c0", "irf_late_c1", "irf_late_c2", "irf_late_c3", "irf_late_c4", "irf_late_c5",
+          "irf_late_c6", "irf_late_c7", "irf_late_t0", "irf_late_t1", "irf_late_t2", "irf_late_t3", "irf_late_t4", "irf_late_t5",
+          "irf_late_t6", "irf_late_t7",
+          "delta_ospp_offsets_0", "delta_ospp_offsets_1", "delta_ospp_offsets_2", "delta_ospp_offsets_3", "delta_ospp_offsets_4",
+          "delta_ospp_coefficients_0", "delta_ospp_coefficients_1", "delta_ospp_coefficients_2", "delta_ospp_coefficients_3",
+          "delta_ospp_coefficients_4", "enable_temp_feedback"},
+         2, -2,
+         // the IRF (scale, switch time, both forms), step count and history bound are per-graph: they define the lag table
+         {0, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 0, 0,
+          0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+          1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0},
+         48, /*n_state*/ 1, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10},
     };
     return k;
 }
@@ -359,7 +415,7 @@ static void emit_program(Graph &g)
     auto node_ref = [](const Node &n) {
         std::ostringstream s;
         s << "rscm_dev::NodeRef{" << (n.rk_table >= 0 ? n.rk_table : 0) << ", " << n.ctab_base << ", " << n.smem_base << ", "
-          << n.scratch_base << "}";
+          << n.scratch_base << ", " << n.gtab_base << ", " << n.aux << "}";
         return s.str();
     };
     o << "    template <class R> __device__ __forceinline__ static void init_state(const R *P, const R *D, R *S,\n"
@@ -500,6 +556,10 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         const KindInfo *k = kind_info(cd.kind);
         if (!k) {
             err = "component kind " + std::to_string(cd.kind) + " has no device implementation (no CPU fallback)";
+            return false;
+        }
+        if (k->bindable.size() != k->param_names.size()) {
+            err = std::string("internal: descriptor table of ") + k->type_name + " is inconsistent";
             return false;
         }
         if (cd.n_params != static_cast<int>(k->param_names.size()) || !cd.params) {
@@ -705,6 +765,14 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
             if (!terr.empty()) { err = terr; return false; }
             g.ctab.insert(g.ctab.end(), tab.begin(), tab.end());
         }
+        n.gtab_base = static_cast<int>(g.gtab.size());
+        if (k->global_table) {
+            std::string terr;
+            const std::vector<double> tab = k->global_table(n.params, g.T, terr);
+            if (!terr.empty()) { err = terr; return false; }
+            g.gtab.insert(g.gtab.end(), tab.begin(), tab.end());
+        }
+        if (k->aux_param >= 0) n.aux = static_cast<int>(n.params[k->aux_param]);
         if (n.kind == RSCM_B200_N2O_CHEMISTRY && !(n.params[4] >= 0.0 && n.params[4] <= 6.0)) {
             err = "N2OChemistry: strat_delay must be in [0, 6] (history ring of the device kernel)";
             return false;

@@ -45,6 +45,9 @@ struct KindInfo {
     std::vector<std::pair<int, int>> in_access = {};
     // per-graph constant table computed on the host from the (non-bindable) geometry parameters
     std::vector<double> (*const_table)(const std::vector<double> &params, std::string &err) = nullptr;
+    // large per-graph table kept in global memory (n_times is passed for tables sized by the run length)
+    std::vector<double> (*global_table)(const std::vector<double> &params, int n_times, std::string &err) = nullptr;
+    int aux_param = -1; // index of an integer parameter handed to the device code as a compile-time literal
 };
 
 const KindInfo *kind_info(int kind);
@@ -70,6 +73,7 @@ struct Node {
     int derived_base = 0; // first derived-constant slot
     int rk_table = -1;    // row of the sub-step table
     int state_base = 0, smem_base = 0, scratch_base = 0, ctab_base = 0; // offsets of this node's stateful storage
+    int gtab_base = 0, aux = 0;
     std::vector<int> in_var, in_src, in_grid;
     std::vector<double> in_factor;
     std::vector<int> out_var, out_grid;
@@ -90,6 +94,7 @@ struct Graph {
     int n_state = 0, n_smem = 0, n_scratch_rows = 0; // stateful components: totals (scratch rows already x T)
     bool needs_time = false;
     std::vector<double> ctab; // concatenated per-graph constant tables (even length)
+    std::vector<double> gtab; // concatenated large tables (global memory)
     std::vector<double> slot_default;
     std::vector<int> slot_bindable;
     std::vector<int> cell_var, cell_region;

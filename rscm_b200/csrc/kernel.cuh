@@ -24,7 +24,7 @@
 
 namespace rscm_dev {
 
-constexpr int MAX_SLOTS = 160;  // component parameter slots per program (KArgs stays below the 4 KB parameter limit)
+constexpr int MAX_SLOTS = 224;  // component parameter slots per program (KArgs stays below the 4 KB parameter limit)
 constexpr int MAX_CELLS = 48;   // scalar storage cells (variables x regions)
 constexpr int MAX_OBS_ROWS = 4; // dense observation tables (one per observed variable)
 
@@ -62,6 +62,7 @@ struct KArgs {
     const double *obs;   // [2][n_obs_rows][Tpad]: values then sigmas (sigma<=0: no observation)
     const double *bounds; // [Tpad + 4] time bounds (T + 1 used), staged only for programs that need the time axis
     const double *ctab;   // [n_ctab] per-graph constant tables of stateful components (host-computed)
+    const double *gtab;   // large per-graph tables that stay in global memory (e.g. the ocean IRF by lag)
     double *scratch;      // [n_scratch][runs] member-interleaved global scratch of stateful components, or null
     int n_ctab;
     int n_exo_rows, n_rk, n_obs_rows;
@@ -84,6 +85,8 @@ struct KArgs {
     double init_def[MAX_CELLS];
     long long out_off[MAX_CELLS]; // byte offset of the cell's first output row (row * runs * 8) or -1
 };
+
+static_assert(sizeof(KArgs) <= 4096, "kernel parameter block must stay within the 4 KB launch limit");
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) -----------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p)
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     cx.nsub = s_nsub;
     cx.bounds = s_bounds;
     cx.ctab = s_ctab;
+    cx.gtab = a.gtab;
     cx.sm = s_thread;
     cx.scratch = a.scratch ? a.scratch + run : nullptr;
     cx.runs = a.runs;

@@ -179,4 +179,73 @@ __device__ __forceinline__ bool n2o_chemistry_solve(const R *P, const R *, const
     return true;
 }
 
+// ---- OceanCarbon — carbon/ocean.rs:167-260: monthly air-sea flux + impulse-response convolution --------------------
+// The reference re-sums the whole monthly flux history against the (nonlinearly scaled) IRF every month:
+// O((12 T)^2 / 2) multiply-adds per run.  Here the scaled IRF is a per-graph table (cx.gtab, lag in months; the IRF
+// parameters are per-graph), the flux history lives in the member-interleaved global scratch, and the history that
+// predates the current year is read ONCE per year while the partial sums of all `steps` months of the year are
+// advanced together (steps FMAs per load) — in the reference's oldest-to-newest order, so the sums are the same
+// up to FMA contraction.  P: see include/rscm_b200.h (60 values); S[0] = months of history so far.
+template <class R> __device__ __forceinline__ void ocean_carbon_prepare(const R *P, R *D)
+{
+    D[0] = P[3] / (P[4] * R(12));            // gas_exchange_rate
+    D[1] = R(1.72e17) / (P[7] * P[8]);       // dic_conversion_factor
+}
+template <class R> __device__ __forceinline__ void ocean_carbon_init_state(const R *, const R *, R *S, const StepCtx<R> &, NodeRef) { S[0] = R(0); }
+
+template <class R>
+__device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R *out, const StepCtx<R> &cx, R *S, NodeRef nr)
+{
+    constexpr int MAXS = 16;
+    const int steps = nr.aux; // steps_per_year: a literal of the emitted program, so the loops below unroll
+    const R co2 = in[0], dsst = in[1];
+    R pco2 = in[2], cumulative = in[3];
+    const R dt = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
+    const R dt_month = dt / R(steps);
+    const R k_gas = D[0], dic_conv = D[1];
+    const int n_old = static_cast<int>(S[0]);
+    const double *irf = cx.gtab + nr.gt;
+    double *hist = cx.scratch + static_cast<long long>(nr.scr) * cx.runs;
+    R acc[MAXS];
+#pragma unroll
+    for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
+    for (int i = 0; i < n_old; ++i) {
+        const R f = R(hist[static_cast<long long>(i) * cx.runs]);
+        const double *w = irf + (n_old - i);
+#pragma unroll
+        for (int m = 0; m < MAXS; ++m)
+            if (m < steps) acc[m] += f * R(__ldg(w + m));
+    }
+    R fy[MAXS];
+    R total_flux = R(0);
+    const R tfac = (P[59] != R(0)) ? r_exp<R>(P[5] * dsst) : R(1);
+#pragma unroll
+    for (int m = 0; m < MAXS; ++m) {
+        if (m < steps) {
+            const R flux_ppm = k_gas * (co2 - pco2);
+            hist[static_cast<long long>(n_old + m) * cx.runs] = static_cast<double>(flux_ppm);
+            fy[m] = flux_ppm;
+            const R flux_gtc_yr = flux_ppm * R(12) * R(2.124);
+            total_flux += flux_gtc_yr / R(steps);
+            cumulative += flux_gtc_yr * dt_month;
+            R integral = acc[m];
+#pragma unroll
+            for (int j = 0; j < MAXS; ++j)
+                if (j <= m) integral += fy[j] * R(__ldg(irf + (m - j)));
+            const R ddic = integral * dic_conv;
+            const R d2 = ddic * ddic, d3 = d2 * ddic, d4 = d2 * d2, d5 = d4 * ddic;
+            const R pw[5] = {ddic, d2 * R(1e-3), -d3 * R(1e-5), d4 * R(1e-7), -d5 * R(1e-10)};
+            R dp = R(0);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) dp += (P[49 + q] + P[54 + q] * P[9]) * pw[q];
+            pco2 = (P[2] + dp) * tfac;
+        }
+    }
+    S[0] = R(n_old + steps);
+    out[0] = total_flux;
+    out[1] = pco2;
+    out[2] = cumulative;
+    return true;
+}
+
 } // namespace rscm_dev

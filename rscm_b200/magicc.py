@@ -9,7 +9,7 @@ from ._builders import ComponentBuilder
 from .core import Component
 
 __all__ = ["GhgForcingBuilder", "OzoneForcingBuilder", "AerosolDirectBuilder", "AerosolIndirectBuilder", "ClimateUDEBBuilder",
-           "CO2BudgetBuilder", "TerrestrialCarbonBuilder", "CH4ChemistryBuilder", "N2OChemistryBuilder"]
+           "CO2BudgetBuilder", "TerrestrialCarbonBuilder", "CH4ChemistryBuilder", "N2OChemistryBuilder", "OceanCarbonBuilder"]
 
 
 class GhgForcingBuilder(ComponentBuilder):
@@ -154,6 +154,81 @@ class N2OChemistryBuilder(ComponentBuilder):
     TYPE_NAME = "N2OChemistry"
     FIELDS = (("n2o_pi", 270.0), ("natural_emissions", 11.0), ("tau_n2o", 139.275), ("lifetime_feedback", -0.04), ("strat_delay", 1),
               ("ppb_to_tg", 4.79))
+
+
+class OceanCarbonBuilder:
+    """OceanCarbonParameters — crates/rscm-magicc/src/parameters/ocean_carbon.rs (presets gfdl_3d / bern_2d / hilda, :150-260).
+
+    ``from_parameters({"model": "3D-GFDL" | "2D-BERN" | "HILDA", ...overrides})``; ``irf_early`` / ``irf_late`` may be given as the
+    reference's tagged dicts ``{"type": "Polynomial", "coefficients": [...]}`` / ``{"type": "ExponentialSum", "coefficients": [...],
+    "timescales": [...]}`` (at most 8 terms).  The flattened block layout is documented in oracle/magicc_ocean.c."""
+
+    TYPE_NAME = "OceanCarbon"
+    _OSPP_OFF = [1.5568, 7.4706, 1.2748, 2.4491, 1.5468]
+    _OSPP_COEF = [-0.013993, -0.20207, -0.12015, -0.12639, -0.15326]
+    _COMMON = dict(co2_pi=278.0, pco2_pi=278.0, gas_exchange_scale=1.833492, temp_sensitivity=0.03717879, irf_scale=0.9492864,
+                   steps_per_year=12, max_history_months=6000, enable_temp_feedback=True)
+    PRESETS = {
+        "3D-GFDL": dict(gas_exchange_tau=7.66, irf_switch_time=1.0, mixed_layer_depth=50.9, ocean_surface_area=3.55e14, sst_pi=17.7,
+                        irf_early={"type": "Polynomial", "coefficients": [1.0, -2.2617, 14.002, -48.770, 82.986, -67.527, 21.037]},
+                        irf_late={"type": "ExponentialSum", "coefficients": [0.01481, 0.019439, 0.038344, 0.066485, 0.24966, 0.70367],
+                                  "timescales": [1.0e10, 347.55, 65.359, 15.281, 2.3488, 0.70177]}),
+        "2D-BERN": dict(gas_exchange_tau=7.46, irf_switch_time=9.9, mixed_layer_depth=50.0, ocean_surface_area=3.5375e14, sst_pi=18.2997,
+                        irf_early={"type": "ExponentialSum", "coefficients": [0.058648, 0.07515, 0.079338, 0.41413, 0.24845, 0.12429],
+                                   "timescales": [1.0e10, 9.6218, 9.2364, 0.7603, 0.16294, 0.0032825]},
+                        irf_late={"type": "ExponentialSum", "coefficients": [0.01369, 0.012456, 0.026933, 0.026994, 0.036608, 0.06738],
+                                  "timescales": [1.0e10, 331.54, 107.57, 38.946, 11.677, 10.515]}),
+        "HILDA": dict(gas_exchange_tau=9.06, irf_switch_time=2.0, mixed_layer_depth=75.0, ocean_surface_area=3.62e14, sst_pi=18.1716,
+                      irf_early={"type": "ExponentialSum", "coefficients": [0.12935, 0.24093, 0.24071, 0.17003, 0.21898],
+                                 "timescales": [1.0e10, 4.9792, 0.96083, 0.26936, 0.034569]},
+                      irf_late={"type": "ExponentialSum", "coefficients": [0.022936, 0.035549, 0.037820, 0.089318, 0.13963, 0.24278],
+                                "timescales": [1.0e10, 232.30, 68.736, 18.601, 5.2528, 1.2679]}),
+    }
+    _MODEL_ID = {"3D-GFDL": 0.0, "2D-BERN": 1.0, "HILDA": 2.0}
+
+    def __init__(self, parameters: dict):
+        self._parameters = dict(parameters)
+
+    @classmethod
+    def from_parameters(cls, parameters: dict):
+        model = parameters.get("model", "3D-GFDL")
+        if model not in cls.PRESETS:
+            raise ValueError(f"OceanCarbon: unknown model {model!r}")
+        known = set(cls._COMMON) | set(cls.PRESETS[model]) | {"model", "delta_ospp_offsets", "delta_ospp_coefficients"}
+        unknown = set(parameters) - known
+        if unknown:
+            raise ValueError(f"OceanCarbon: unknown parameter(s) {sorted(unknown)}")
+        return cls(parameters)
+
+    @staticmethod
+    def _flatten_irf(form: dict) -> list:
+        coef = list(form["coefficients"])
+        tau = list(form.get("timescales", []))
+        kind = {"Polynomial": 0.0, "ExponentialSum": 1.0}[form["type"]]
+        if len(coef) > 8 or (kind == 1.0 and len(tau) != len(coef)):
+            raise ValueError("OceanCarbon: IRF forms take at most 8 terms with matching timescales")
+        return [kind, float(len(coef))] + coef + [0.0] * (8 - len(coef)) + (tau + [1.0] * (8 - len(tau)))
+
+    def build(self) -> Component:
+        model = self._parameters.get("model", "3D-GFDL")
+        p = {**self._COMMON, **self.PRESETS[model], "delta_ospp_offsets": self._OSPP_OFF, "delta_ospp_coefficients": self._OSPP_COEF}
+        p.update({k: v for k, v in self._parameters.items() if k != "model"})
+        vals = [self._MODEL_ID[model], p["co2_pi"], p["pco2_pi"], p["gas_exchange_scale"], p["gas_exchange_tau"], p["temp_sensitivity"],
+                p["irf_scale"], p["mixed_layer_depth"], p["ocean_surface_area"], p["sst_pi"], p["steps_per_year"], p["max_history_months"],
+                p["irf_switch_time"]]
+        vals += self._flatten_irf(p["irf_early"]) + self._flatten_irf(p["irf_late"])
+        vals += list(p["delta_ospp_offsets"]) + list(p["delta_ospp_coefficients"]) + [1.0 if p["enable_temp_feedback"] else 0.0]
+        names = (["model", "co2_pi", "pco2_pi", "gas_exchange_scale", "gas_exchange_tau", "temp_sensitivity", "irf_scale", "mixed_layer_depth",
+                  "ocean_surface_area", "sst_pi", "steps_per_year", "max_history_months", "irf_switch_time"]
+                 + [f"irf_{w}_{f}" for w in ("early", "late") for f in (["kind", "n"] + [f"c{i}" for i in range(8)] + [f"t{i}" for i in range(8)])]
+                 + [f"delta_ospp_offsets_{i}" for i in range(5)] + [f"delta_ospp_coefficients_{i}" for i in range(5)] + ["enable_temp_feedback"])
+        # the emitter's name order interleaves early/late per form; rebuild it exactly as graph.cpp lists it
+        names = (names[:13]
+                 + ["irf_early_kind", "irf_early_n"] + [f"irf_early_c{i}" for i in range(8)] + [f"irf_early_t{i}" for i in range(8)]
+                 + ["irf_late_kind", "irf_late_n"] + [f"irf_late_c{i}" for i in range(8)] + [f"irf_late_t{i}" for i in range(8)]
+                 + names[-11:])
+        assert len(vals) == 60 and len(names) == 60
+        return Component(_ffi.OCEAN_CARBON, self.TYPE_NAME, names, vals)
 
 
 class ClimateUDEBBuilder(_ArrayFieldsBuilder):

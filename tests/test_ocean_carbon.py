@@ -1,0 +1,168 @@
+"""OceanCarbon (impulse-response ocean carbon cycle with an O(T^2) flux-history convolution) and the full
+emissions-driven MAGICC graph of the reference's regression suite (tests/regression/test_ghg_forcing.py:470-620,
+minus HalocarbonChemistry): oracle known answers on CPU, GPU parity at 1e-9."""
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from rscm_b200 import synthetic as syn
+from rscm_b200.core import GridType, ModelBuilder, VariableSchema
+from rscm_b200.magicc import (AerosolDirectBuilder, AerosolIndirectBuilder, CH4ChemistryBuilder, ClimateUDEBBuilder, CO2BudgetBuilder,
+                              GhgForcingBuilder, N2OChemistryBuilder, OceanCarbonBuilder, OzoneForcingBuilder, TerrestrialCarbonBuilder)
+
+from .helpers import oracle_bindings, oracle_from_builder, rel_err
+
+
+def ocean_builder(model="3D-GFDL", start=1850, end=1950):
+    return (ModelBuilder().with_time_axis(syn.time_axis(start, end))
+            .with_rust_component(OceanCarbonBuilder.from_parameters({"model": model}).build())
+            .with_initial_values({"Ocean Surface pCO2": 278.0, "Cumulative Ocean Uptake": 0.0}))
+
+
+def ocean_scenario(start=1850, end=1950, scale=1.0):
+    years = syn.time_axis(start, end).values()
+    return {"Atmospheric Concentration|CO2": 278.0 * np.exp(0.004 * scale * (years - start)), "Sea Surface Temperature": 0.01 * (years - start)}
+
+
+# ---- oracle known answers: crates/rscm-magicc/src/parameters/ocean_carbon.rs and carbon/ocean.rs unit tests ----
+def _irf(model, t):
+    import ctypes
+    comp = OceanCarbonBuilder.from_parameters({"model": model}).build()
+    p = np.array(comp.params)
+    L = orc.lib()
+    L.orc_ocean_irf.restype = ctypes.c_double
+    L.orc_ocean_irf.argtypes = [ctypes.c_void_p, ctypes.c_double]
+    return L.orc_ocean_irf(orc._dp(p), t)
+
+
+def test_irf_presets_behave_like_the_reference_tests():
+    assert _irf("HILDA", 0.0) > 0.9 and _irf("HILDA", 100.0) < _irf("HILDA", 10.0) < _irf("HILDA", 0.0) and _irf("HILDA", 100.0) > 0.0
+    for model, sw in (("3D-GFDL", 1.0), ("2D-BERN", 9.9), ("HILDA", 2.0)):
+        before, after = _irf(model, sw - 1e-6), _irf(model, sw + 1e-6)
+        assert 0.0 < before < 1.5 and 0.0 < after < 1.5 and 0.1 < before / after < 10.0
+    assert _irf("3D-GFDL", 0.0) == pytest.approx(1.0)  # polynomial IRF starts at 1; scaling keeps 1 -> 1
+
+
+@pytest.mark.parametrize("model", ["3D-GFDL", "2D-BERN", "HILDA"])
+def test_ocean_uptake_follows_atmospheric_co2(model):
+    b = ocean_builder(model, end=1900)
+    r = oracle_from_builder(b, ocean_scenario(end=1900)).run()
+    flux, pco2, cum = r["Carbon Flux|Ocean"], r["Ocean Surface pCO2"], r["Cumulative Ocean Uptake"]
+    assert np.isnan(flux[0]) and pco2[0] == 278.0 and cum[0] == 0.0
+    assert flux[1] == 0.0                        # equilibrium in the first year: atm = ocean pCO2 (test_zero_flux_at_equilibrium)
+    assert np.all(flux[3:] > 0.0) and np.all(np.diff(cum[2:]) > 0.0)   # atm > ocean drives uptake
+    assert np.all(pco2[3:] > 278.0) and np.all(pco2[3:] < r["Atmospheric Concentration|CO2"][3:])
+    np.testing.assert_allclose(np.diff(cum)[1:], flux[2:], rtol=1e-12)  # cumulative integrates the annual-mean flux (dt = 1)
+
+
+def test_equilibrium_stays_at_rest():
+    b = ocean_builder(end=1870)
+    r = oracle_from_builder(b, {"Atmospheric Concentration|CO2": np.full(21, 278.0), "Sea Surface Temperature": np.zeros(21)}).run()
+    assert np.all(r["Carbon Flux|Ocean"][1:] == 0.0) and np.all(r["Ocean Surface pCO2"] == 278.0)
+
+
+def test_history_limit_is_refused_by_the_engine():
+    from rscm_b200 import _ffi
+    b = (ModelBuilder().with_time_axis(syn.time_axis(1850, 2100))
+         .with_rust_component(OceanCarbonBuilder.from_parameters({"max_history_months": 120}).build())
+         .with_initial_values({"Ocean Surface pCO2": 278.0, "Cumulative Ocean Uptake": 0.0}))
+    with pytest.raises(_ffi.EngineError, match="max_history_months"):
+        b.build_ensemble(device=-2)
+
+
+# ---- GPU parity ---------------------------------------------------------------------------------------------------
+OCEAN_BINDS = {"tau": "OceanCarbon.gas_exchange_tau", "sst_pi": "OceanCarbon.sst_pi", "ts": "OceanCarbon.temp_sensitivity",
+               "mld": "OceanCarbon.mixed_layer_depth"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["3D-GFDL", "HILDA"])
+def test_ocean_carbon_gpu_parity(model, tmp_path, monkeypatch):
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    b = ocean_builder(model, end=1950)
+    ens = b.build_ensemble().bind_parameters(OCEAN_BINDS)
+    sc = ens.pack_scenarios([ocean_scenario(), ocean_scenario(scale=1.5)])
+    p = syn.uniform_params({"tau": (6.0, 10.0), "sst_pi": (17.0, 19.0), "ts": (0.03, 0.045), "mld": (45.0, 80.0)}, 96, 31)
+    got = ens.split_outputs(ens.run(p, sc))
+    m = oracle_from_builder(b)
+    names = ens.variable_names
+    ref = m.split(m.run_batch(oracle_bindings(b, OCEAN_BINDS), p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
+
+
+def full_magicc_builder(start=1850, end=1950):
+    """Emissions-driven MAGICC: CH4/N2O chemistry, terrestrial + ocean carbon, CO2 budget, GHG / ozone / aerosol forcing,
+    Sum aggregate (with an initial value), ClimateUDEB on the four-box grid."""
+    schema = VariableSchema()
+    for n in ("CH4", "N2O", "NOx", "CO", "NMVOC", "SOx", "BC", "OC", "CO2|Fossil", "CO2|Land Use"):
+        schema.add_variable(f"Emissions|{n}", "")
+    schema.add_variable("EESC", "ppt")
+    for n in ("CO2", "CH4", "N2O"):
+        schema.add_variable(f"Atmospheric Concentration|{n}", "")
+    for n in syn.CONFIG4_ERF_PARTS:
+        schema.add_variable(n, "W/m^2")
+    schema.add_variable("Surface Temperature", "K", GridType.FourBox)
+    for n in ("Heat Uptake", "Ocean Heat Content", "Sea Surface Temperature", "Carbon Flux|Terrestrial", "Carbon Flux|Ocean", "Carbon Pool|Plant",
+              "Carbon Pool|Detritus", "Carbon Pool|Soil", "Carbon Pool|Humus", "Ocean Surface pCO2", "Cumulative Ocean Uptake",
+              "Emissions|CO2|Net", "Airborne Fraction|CO2", "Lifetime|CH4", "Lifetime|N2O"):
+        schema.add_variable(n, "")
+    schema.add_aggregate("Effective Radiative Forcing", "W/m^2", "Sum", syn.CONFIG4_ERF_PARTS)
+    return (
+        ModelBuilder().with_time_axis(syn.time_axis(start, end)).with_schema(schema)
+        .with_rust_component(CH4ChemistryBuilder.from_parameters({}).build())
+        .with_rust_component(N2OChemistryBuilder.from_parameters({}).build())
+        .with_rust_component(TerrestrialCarbonBuilder.from_parameters({}).build())
+        .with_rust_component(OceanCarbonBuilder.from_parameters({}).build())
+        .with_rust_component(CO2BudgetBuilder.from_parameters({}).build())
+        .with_rust_component(GhgForcingBuilder.from_parameters({"method": "Ipcctar"}).build())
+        .with_rust_component(OzoneForcingBuilder.from_parameters({}).build())
+        .with_rust_component(AerosolDirectBuilder.from_parameters({}).build())
+        .with_rust_component(AerosolIndirectBuilder.from_parameters({}).build())
+        .with_rust_component(ClimateUDEBBuilder.from_parameters({}).build())
+        .with_initial_values({"Atmospheric Concentration|CH4": 722.0, "Atmospheric Concentration|N2O": 270.0,
+                              "Atmospheric Concentration|CO2": 278.0, "Carbon Pool|Plant": 884.86, "Carbon Pool|Detritus": 92.77,
+                              "Carbon Pool|Soil": 1681.53, "Carbon Pool|Humus": 836.0, "Ocean Surface pCO2": 278.0,
+                              "Cumulative Ocean Uptake": 0.0, "Surface Temperature": 0.0, "Effective Radiative Forcing": 0.0,
+                              "Sea Surface Temperature": 0.0, "Carbon Flux|Terrestrial": 0.0, "Carbon Flux|Ocean": 0.0})
+    )
+
+
+def full_magicc_scenario(start=1850, end=1950, f=1.0):
+    years = syn.time_axis(start, end).values()
+    ramp = (years - start) / 100.0
+    return {"Emissions|CH4": 50.0 + 250.0 * ramp * f, "Emissions|N2O": 1.0 + 6.0 * ramp, "Emissions|NOx": 5.0 + 30.0 * ramp,
+            "Emissions|CO": 100.0 + 500.0 * ramp, "Emissions|NMVOC": 20.0 + 100.0 * ramp, "Emissions|SOx": 1.0 + 50.0 * ramp,
+            "Emissions|BC": 2.5 + 4.0 * ramp, "Emissions|OC": 10.0 + 15.0 * ramp, "Emissions|CO2|Fossil": 8.0 * ramp ** 2 * f,
+            "Emissions|CO2|Land Use": 0.5 + 0.8 * ramp, "EESC": 1000.0 + 900.0 * ramp}
+
+
+FULL_BINDS = {"ecs": "ClimateUDEB.ecs", "beta": "TerrestrialCarbon.beta", "tau": "OceanCarbon.gas_exchange_tau", "tau_oh": "CH4Chemistry.tau_oh"}
+
+
+def test_full_magicc_graph_on_the_oracle():
+    b = full_magicc_builder(end=1900)
+    m = oracle_from_builder(b, full_magicc_scenario(end=1900))
+    ens = b.build_ensemble(device=-2)
+    assert ens.execution_order() == m.execution_order() and ens.variable_names == m.names and ens.program_is_jit()
+    r = m.run()
+    assert r["Atmospheric Concentration|CO2"][-1] > 285.0 and r["Atmospheric Concentration|CH4"][-1] > 900.0
+    assert np.all(np.isfinite(r["Surface Temperature"])) and abs(r["Surface Temperature"][-1].mean()) > 0.01
+    assert r["Cumulative Ocean Uptake"][-1] > 0.0
+
+
+@pytest.mark.gpu
+def test_full_magicc_gpu_parity(tmp_path, monkeypatch):
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    b = full_magicc_builder()
+    ens = b.build_ensemble().bind_parameters(FULL_BINDS)
+    sc = ens.pack_scenarios([full_magicc_scenario(), full_magicc_scenario(f=1.3)])
+    p = syn.uniform_params({"ecs": (2.0, 4.5), "beta": (0.4, 0.9), "tau": (6.5, 9.5), "tau_oh": (8.5, 10.5)}, 64, 41)
+    got = ens.split_outputs(ens.run(p, sc))
+    m = oracle_from_builder(b)
+    names = ens.variable_names
+    ref = m.split(m.run_batch(oracle_bindings(b, FULL_BINDS), p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
+    assert np.isfinite(got["Surface Temperature"]).all()
