@@ -9,13 +9,14 @@
 // One thread = one member.  Where the state lives:
 //   * S[20]      (registers): LAMCALC result at the member's base ECS, upwelling rates, land / ground
 //                temperatures, alpha_eff, inter-hemispheric exchange, history length;
-//   * cx.sm      (shared memory, [150][BLOCK] per CTA, conflict-free): the two 50-layer ocean columns and
-//                the Thomas sweep's c' array — the tridiagonal rows are built on the fly, d' overwrites T;
+//   * cx.sm      (shared memory, [50][4][BLOCK] per CTA, conflict-free): the two 50-layer ocean columns and
+//                the two Thomas sweeps' c' arrays — the tridiagonal rows are built on the fly, d' overwrites T;
 //   * cx.scratch (global, member-interleaved [T][runs]): the T*dt history of the cumulative-temperature
 //                feedback, summed newest-to-oldest in the reference's order;
-//   * cx.ctab    (shared memory, per graph): area factors af_top/af_bottom/af_diff and the initial ocean
-//                profile of both hemispheres — they depend only on geometry parameters, which are
-//                per-graph (not bindable per member), so the host computes them once.
+//   * cx.ctab    (shared memory, per graph): area factors af_top/af_bottom/af_diff, the entrainment
+//                combinations of the initial ocean profile of both hemispheres and the relative-depth factor
+//                of the diffusivity profile — they depend only on geometry parameters, which are
+//                per-graph (not bindable per member), so the host computes them once (graph.cpp).
 #pragma once
 
 namespace rscm_dev {
@@ -29,40 +30,29 @@ enum { US_OK, US_LAMO, US_LAML, US_EFF, US_QF0, US_QF1, US_QF2, US_QF3, US_W0, U
        US_AE0, US_AE1, US_HX0, US_HX1, US_NHIST, US_N };
 
 constexpr int UDEB_MAXL = 50;
+constexpr int UDEB_ROW = 4 * BLOCK; // per-thread scratch: values per layer and CTA {T_nh, T_sh, c'_nh, c'_sh}
+constexpr int UDEB_CT = 6;          // constant table: values per layer
 
-template <class R> __device__ __forceinline__ R r_min(R a, R b) { return (b < a || a != a) ? b : a; } // f64::min: NaN-ignoring
-template <class R> __device__ __forceinline__ R r_max(R a, R b) { return (b > a || a != a) ? b : a; }
+// f64::min / f64::max: NaN-ignoring, like fmin / fmax
+__device__ __forceinline__ double r_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float r_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double r_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float r_max(float a, float b) { return fmaxf(a, b); }
 
-// invert_4x4 — Gauss-Jordan with partial pivoting
-template <class R> __device__ inline bool udeb_invert4(const R (&m)[4][4], R (&inv)[4][4])
+// Reciprocal for the Thomas sweep: the pivots of the diagonally dominant ocean-column system are >= 1, never
+// subnormal or infinite, so the special-case slow path of 1/x (a divergent call that also keeps the compiler from
+// interleaving the two hemispheres' recurrences) is dropped: MUFU seed (~2^-20) + two Newton steps (<= 1 ulp; a NaN
+// pivot stays NaN).
+__device__ __forceinline__ double r_rcp(double x)
 {
-    R aug[4][8];
-    for (int i = 0; i < 4; ++i) {
-        for (int j = 0; j < 4; ++j) { aug[i][j] = m[i][j]; aug[i][j + 4] = R(0); }
-        aug[i][i + 4] = R(1);
-    }
-    for (int col = 0; col < 4; ++col) {
-        int max_row = col;
-        R max_val = r_abs(aug[col][col]);
-        for (int row = col + 1; row < 4; ++row) {
-            const R v = r_abs(aug[row][col]);
-            if (v > max_val) { max_val = v; max_row = row; }
-        }
-        if (max_val < R(1e-15)) return false;
-        if (max_row != col)
-            for (int j = 0; j < 8; ++j) { const R t = aug[col][j]; aug[col][j] = aug[max_row][j]; aug[max_row][j] = t; }
-        const R pivot = aug[col][col];
-        for (int j = 0; j < 8; ++j) aug[col][j] /= pivot;
-        for (int row = 0; row < 4; ++row) {
-            if (row == col) continue;
-            const R f = aug[row][col];
-            for (int j = 0; j < 8; ++j) aug[row][j] -= f * aug[col][j];
-        }
-    }
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) inv[i][j] = aug[i][j + 4];
-    return true;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
 }
+__device__ __forceinline__ float r_rcp(float x) { return __frcp_rn(x); }
 
 template <class R> __device__ __forceinline__ void udeb_fractions(const R *P, R (&a)[4])
 {
@@ -77,7 +67,13 @@ template <class R> __device__ __forceinline__ void udeb_qfrac(const R *P, const 
     for (int i = 0; i < 4; ++i) q[i] = (r_abs(s) <= R(1e-15)) ? R(1) : P[U_RFR0 + i] / s;
 }
 
-// lamcalc — hybrid step / secant iteration on lambda_ocean, tolerance 1e-3 on the land/ocean warming ratio
+// lamcalc — hybrid step / secant iteration on lambda_ocean, tolerance 1e-3 on the land/ocean warming ratio.
+// The reference inverts the 4x4 box-coupling matrix by Gauss-Jordan (linear_algebra.rs:102-166); its sparsity
+//   [ A0      -k_lo   -k_ns    0    ]      rows 1 and 3 couple each land box to its own ocean box only,
+//   [ -k_lo*a  B1      0       0    ]      so eliminating them leaves a 2x2 system in the two ocean boxes,
+//   [ -k_ns    0       A2     -k_lo ]      solved here by Cramer's rule (same solution up to rounding; the
+//   [ 0        0      -k_lo*a  B3   ]      singular-pivot failure becomes a vanishing B1, B3 or determinant).
+// Only the last three iterates of the reference's lamo[]/diff[] arrays are ever read: kept as scalars.
 template <class R> __device__ inline bool udeb_lamcalc(const R *P, R ecs, R &lam_o_out, R &lam_l_out, R &eff_out)
 {
     constexpr int MAXIT = 40;
@@ -88,53 +84,50 @@ template <class R> __device__ inline bool udeb_lamcalc(const R *P, R ecs, R &lam
     const R fgno = area[0], fgnl = area[1], fgso = area[2], fgsl = area[3];
     const R lam = q2x / ecs;
     const R fratio = (fgno + fgso) / (fgnl + fgsl);
-    R lamo[MAXIT + 2], diff[MAXIT + 2];
-    for (int i = 0; i < MAXIT + 2; ++i) { lamo[i] = R(0); diff[i] = R(0); }
-    lamo[1] = lam;
-    lamo[2] = lam + R(0.7);
+    const R f0 = q2x * area[0] * qfrac[0], f1 = q2x * area[1] * qfrac[1], f2 = q2x * area[2] * qfrac[2], f3 = q2x * area[3] * qfrac[3];
+    const R kla = k_lo * alpha, inv_o = R(1) / (fgno + fgso), inv_l = R(1) / (fgnl + fgsl);
+    R l0 = R(0), l1 = lam, l2 = lam + R(0.7); // lamo[i-2], lamo[i-1], lamo[i]
+    R d0 = R(0), d1 = R(0);                    // diff[i-2], diff[i-1]
     R dlamo = R(0.7);
-    int iflag = 0;
+    bool bracketed = false;
     for (int i = 2; i <= MAXIT; ++i) {
-        const R lam_l = lam + fratio * (lam - lamo[i]) / rlo;
-        const R lam_o = lamo[i];
-        const R mtx[4][4] = {{fgno * lam_o + k_lo * alpha + k_ns, -k_lo, -k_ns, R(0)},
-                             {-k_lo * alpha, fgnl * lam_l + k_lo, R(0), R(0)},
-                             {-k_ns, R(0), fgso * lam_o + k_lo * alpha + k_ns, -k_lo},
-                             {R(0), R(0), -k_lo * alpha, fgsl * lam_l + k_lo}};
-        R inv[4][4];
-        if (!udeb_invert4(mtx, inv)) return false;
-        R temps[4];
-        for (int r = 0; r < 4; ++r) {
-            R s = R(0);
-            for (int c = 0; c < 4; ++c) s += inv[r][c] * area[c] * qfrac[c];
-            temps[r] = q2x * s;
-        }
-        const R ocean_mean = (fgno * temps[0] + fgso * temps[2]) / (fgno + fgso);
-        const R land_mean = (fgnl * temps[1] + fgsl * temps[3]) / (fgnl + fgsl);
-        diff[i] = rlo - land_mean / ocean_mean;
-        if (r_abs(diff[i]) < R(0.001)) {
+        const R lam_o = l2;
+        const R lam_l = lam + fratio * (lam - lam_o) / rlo;
+        const R B1 = fgnl * lam_l + k_lo, B3 = fgsl * lam_l + k_lo;
+        if (r_abs(B1) < R(1e-15) || r_abs(B3) < R(1e-15)) return false;
+        const R r1 = R(1) / B1, r3 = R(1) / B3;
+        const R a00 = fgno * lam_o + kla + k_ns - k_lo * kla * r1;
+        const R a22 = fgso * lam_o + kla + k_ns - k_lo * kla * r3;
+        const R g0 = f0 + k_lo * f1 * r1, g2 = f2 + k_lo * f3 * r3;
+        const R det = a00 * a22 - k_ns * k_ns;
+        if (r_abs(det) < R(1e-15)) return false;
+        const R rd = R(1) / det;
+        const R t0 = (g0 * a22 + k_ns * g2) * rd, t2 = (a00 * g2 + k_ns * g0) * rd;
+        const R t1 = (f1 + kla * t0) * r1, t3 = (f3 + kla * t2) * r3;
+        const R ocean_mean = (fgno * t0 + fgso * t2) * inv_o;
+        const R land_mean = (fgnl * t1 + fgsl * t3) * inv_l;
+        const R d2 = rlo - land_mean / ocean_mean;
+        if (r_abs(d2) < R(0.001)) {
             R rf_sum = R(0);
             for (int c = 0; c < 4; ++c) rf_sum += P[U_RFR0 + c] * area[c];
             R eff = R(1);
-            if (r_abs(rf_sum) > R(1e-15)) {
-                R tg = R(0);
-                for (int r = 0; r < 4; ++r) tg += area[r] * temps[r];
-                eff = tg / ecs;
-            }
+            if (r_abs(rf_sum) > R(1e-15)) eff = (area[0] * t0 + area[1] * t1 + area[2] * t2 + area[3] * t3) / ecs;
             lam_o_out = lam_o; lam_l_out = lam_l; eff_out = eff;
             return true;
         }
-        if (diff[i] * diff[i - 1] < R(0)) iflag = 1;
-        if (iflag == 0) {
-            if (r_abs(diff[i]) > r_abs(diff[i - 1])) dlamo = -dlamo;
-            lamo[i + 1] = lamo[i] + dlamo;
-        } else if (diff[i] * diff[i - 1] < R(0)) {
-            const R den = diff[i] - diff[i - 1];
-            lamo[i + 1] = (r_abs(den) < R(1e-30)) ? lamo[i] + dlamo : lamo[i] - diff[i] * (lamo[i] - lamo[i - 1]) / den;
+        const bool flip = d2 * d1 < R(0);
+        bracketed = bracketed || flip;
+        R next;
+        if (!bracketed) {
+            if (r_abs(d2) > r_abs(d1)) dlamo = -dlamo;
+            next = l2 + dlamo;
         } else {
-            const R den = diff[i] - diff[i - 2];
-            lamo[i + 1] = (r_abs(den) < R(1e-30)) ? lamo[i] + dlamo : lamo[i] - diff[i] * (lamo[i] - lamo[i - 2]) / den;
+            const R dref = flip ? d1 : d0, lref = flip ? l1 : l0;
+            const R den = d2 - dref;
+            next = (r_abs(den) < R(1e-30)) ? l2 + dlamo : l2 - d2 * (l2 - lref) / den;
         }
+        l0 = l1; l1 = l2; l2 = next;
+        d0 = d1; d1 = d2;
     }
     return false;
 }
@@ -192,100 +185,101 @@ template <class R> __device__ inline void climate_udeb_init_state(const R *P, co
     S[US_AE0] = S[US_AE1] = P[U_TA_ALPHA];
     S[US_HX0] = S[US_HX1] = R(0);
     S[US_NHIST] = R(0);
-    R *T = cx.sm + nr.sm * BLOCK;
-    for (int i = 0; i < 2 * n; ++i) T[i * BLOCK] = R(0);
+    R *col = cx.sm + nr.sm * BLOCK;
+    for (int i = 0; i < n; ++i) col[i * UDEB_ROW] = col[i * UDEB_ROW + BLOCK] = R(0);
 }
 
-// step_hemisphere: build the tridiagonal rows on the fly, Thomas forward sweep (c' to shared memory, d' over T),
-// back substitution, temperature cap.  T = this thread's column (stride BLOCK), cp = this thread's c' array.
-template <class R>
-__device__ inline R udeb_step_hemisphere(const R *P, const R *S, const double *ctab, R *T, R *cp, int hemi, R forcing, R dt, R lam_o,
-                                         R lam_l, R hx, R ground_temp, R alpha_eff)
-{
-    const int n = static_cast<int>(P[U_NLAYERS]);
-    const double *aft = ctab, *afb = ctab + n, *afd = ctab + 2 * n, *init = ctab + (3 + hemi) * n;
-    const R dz = P[U_DZ], dz_mix = P[U_MLD], pi_ratio = P[U_PI_RATIO], w = S[US_W0 + hemi];
-    const R conv = R(3155.76); // DIFFUSIVITY_CM2S_TO_M2YR
-    const R total_depth = dz_mix + (R(n) - R(1)) * dz;
-    const R t_top = T[0], t_bottom = T[(n - 1) * BLOCK];
-    const R kmin = P[U_KAPPA_MIN] * conv;
-    const R dk = P[U_KAPPA_DKDT] * (t_top - t_bottom);
-    // kappa at the boundary below layer l
-    auto kappa = [&](int l) -> R {
-        const R rel = (dz_mix + R(l) * dz) / total_depth;
-        return r_max(((R(1) - rel) * dk + P[U_KAPPA]) * conv, kmin);
-    };
-    const R c_mix = udeb_heat_capacity(dz_mix);
-    const R f_l = (hemi == 0 ? P[U_NH_LAND] : P[U_SH_LAND]) / R(2);
-    const R f_o = R(0.5) - f_l;
-    const R denominator = f_o * (P[U_KLO] + f_l * lam_l);
-    const R term_feedback = alpha_eff / c_mix * (lam_o + lam_l * P[U_KLO] * P[U_AMP] * f_l / denominator);
-    const R dz1 = dz / R(2);
-    const R forcing_amp = R(1) + P[U_KLO] * f_l / denominator;
-    const R delta_w = w - P[U_W0];
-    const bool dw = r_abs(delta_w) > R(1e-15);
-    const R tp = R(1); // polar_sinking_temp (state.rs default)
-    const R dtdz = dt / dz;
-    const R t0 = t_top; // mixed-layer temperature before the solve (entrainment terms)
+// Constants of one model year for step_hemisphere (everything that does not change between sub-steps).
+template <class R> struct UdebYear {
+    R cA, cA1, cM, dt_mix, dtdz, dt_cmix, kc, kmin, dkdt_c, pi_ratio, tmax;
+    R tfb_dt[2], famp[2], lhc_c[2]; // per hemisphere
+    bool lhc;
+};
 
-    // row 0
-    R k_prev = kappa(0);
-    R cprev, dprev;
-    {
-        const R term_diff = k_prev / (dz_mix * dz1) * dt;
-        const R term_upwell = w / dz_mix * dt;
-        const R b0 = R(1) + term_feedback * dt * R(aft[0]) + term_diff * R(afb[0]) + term_upwell * pi_ratio * R(afb[0]);
-        const R c0 = -(term_diff + term_upwell) * R(afb[0]);
-        R d0 = t0 + (forcing * forcing_amp + hx) / c_mix * dt * R(aft[0]);
-        if (P[U_LHC_ON] != R(0)) d0 -= P[U_KLG] * (S[US_LAND0 + hemi] - ground_temp) / (c_mix * f_o) * dt * R(aft[0]);
-        if (dw) d0 += dt / dz_mix * delta_w * (R(init[1]) - tp) * R(afb[0]);
-        cprev = c0 / b0;
-        dprev = d0 / b0;
-        cp[0] = cprev;
-        T[0] = dprev;
+// step_hemisphere for both hemispheres at once (they only exchange heat through the previous sub-step's state, so
+// the two Thomas recurrences are independent and interleaving them doubles the instruction-level parallelism).
+// Rows are built on the fly; the forward sweep keeps -c' in the per-thread c' column and d' over T; one
+// reciprocal per row; back substitution on the uncapped solution, the cap applies to what is stored.
+// col = this thread's scratch, layer-major: layer i holds {T_nh, T_sh, c'_nh, c'_sh} at col[(4*i + k) * BLOCK].
+// ctab = per layer {af_top, af_bottom, af_diff, omr, g_nh, g_sh} (graph.cpp udeb_const_table).
+
+template <class R>
+__device__ __forceinline__ void udeb_step_both(const UdebYear<R> &y, const R *P, R *S, const double *ctab, int n, R *col, R forcing_nh,
+                                               R forcing_sh)
+{
+    const R forcing[2] = {forcing_nh, forcing_sh};
+    R dkc[2], tul[2], pt0[2], dwc[2], kprev[2], cneg[2], dp[2];
+    const R at0 = R(ctab[0]), ab0 = R(ctab[1]), om0 = R(ctab[3]);
+    R *bottom = col + (n - 1) * UDEB_ROW;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const R w = S[US_W0 + h];
+        const R t0 = col[h * BLOCK]; // mixed-layer temperature before the solve (entrainment terms)
+        dkc[h] = y.dkdt_c * (t0 - bottom[h * BLOCK]);
+        const R delta_w = w - P[U_W0];
+        const R dwv = (r_abs(delta_w) > R(1e-15)) ? delta_w : R(0);
+        dwc[h] = y.dtdz * dwv;
+        tul[h] = w * y.dtdz;
+        pt0[h] = y.pi_ratio * tul[h] * t0;
+        // row 0: mixed layer
+        const R k0 = r_max(om0 * dkc[h] + y.kc, y.kmin);
+        const R term_diff = k0 * y.cM, term_upwell = w * y.dt_mix;
+        const R b0 = R(1) + y.tfb_dt[h] * at0 + term_diff * ab0 + term_upwell * y.pi_ratio * ab0;
+        R d0 = t0 + (forcing[h] * y.famp[h] + S[US_HX0 + h]) * y.dt_cmix * at0;
+        if (y.lhc) d0 -= y.lhc_c[h] * (S[US_LAND0 + h] - S[US_GR0 + h]) * at0;
+        d0 += y.dt_mix * dwv * R(ctab[4 + h]);
+        const R r = r_rcp(b0);
+        cneg[h] = (term_diff + term_upwell) * ab0 * r;
+        dp[h] = d0 * r;
+        col[(2 + h) * BLOCK] = cneg[h];
+        col[h * BLOCK] = dp[h];
+        kprev[h] = k0;
     }
-    const R tul = w / dz * dt;
-    for (int i = 1; i < n - 1; ++i) {
-        const R dz_up = (i == 1) ? dz1 : dz;
-        const R k_i = kappa(i);
-        const R tdu = k_prev / (dz * dz_up) * dt;
-        const R tdd = k_i / (dz * dz) * dt;
-        const R at = R(aft[i]), ab = R(afb[i]), ad = R(afd[i]);
-        const R ai = -tdu * at;
-        const R bi = R(1) + tdu * at + tdd * ab + tul * at;
-        const R ci = -(tdd + tul) * ab;
-        R di = T[i * BLOCK] + pi_ratio * tul * t0 * ad;
-        if (dw) {
-            di += dtdz * delta_w * (R(init[i + 1]) * ab - R(init[i]) * at);
-            di += dtdz * delta_w * tp * ad;
+    R cu = y.cA1; // 1/(dz*dz_up): the layer below the mixed layer sees half a layer thickness upwards
+    R *row = col + UDEB_ROW;
+    const double *ct = ctab + UDEB_CT;
+#pragma unroll 2
+    for (; row != bottom; row += UDEB_ROW, ct += UDEB_CT) {
+        const double2 c01 = *reinterpret_cast<const double2 *>(ct), c23 = *reinterpret_cast<const double2 *>(ct + 2),
+                      c45 = *reinterpret_cast<const double2 *>(ct + 4); // 48-byte rows: 16-byte aligned
+        const R at = R(c01.x), ab = R(c01.y), ad = R(c23.x), om = R(c23.y);
+        const R gh[2] = {R(c45.x), R(c45.y)};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const R k_i = r_max(om * dkc[h] + y.kc, y.kmin);
+            const R m = kprev[h] * cu * at; // -a_i
+            const R tdd = k_i * y.cA;
+            const R bi = R(1) + m + tdd * ab + tul[h] * at;
+            const R di = row[h * BLOCK] + pt0[h] * ad + dwc[h] * gh[h];
+            const R r = r_rcp(bi - m * cneg[h]);
+            cneg[h] = (tdd + tul[h]) * ab * r;
+            dp[h] = (di + m * dp[h]) * r;
+            row[(2 + h) * BLOCK] = cneg[h];
+            row[h * BLOCK] = dp[h];
+            kprev[h] = k_i;
         }
-        const R den = bi - ai * cprev;
-        cprev = ci / den;
-        dprev = (di - ai * dprev) / den;
-        cp[i * BLOCK] = cprev;
-        T[i * BLOCK] = dprev;
-        k_prev = k_i;
+        cu = y.cA;
     }
     {
-        const int i = n - 1;
-        const R tdu = k_prev / (dz * dz) * dt;
-        const R at = R(aft[i]);
-        const R ai = -tdu * at;
-        const R bi = R(1) + (tdu + tul) * at;
-        R di = T[i * BLOCK] + pi_ratio * tul * t0 * at;
-        if (dw) di += dtdz * delta_w * (tp - R(init[i])) * at;
-        const R den = bi - ai * cprev;
-        dprev = (di - ai * dprev) / den;
+        const R at = R(ct[0]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const R m = kprev[h] * y.cA * at;
+            const R bi = R(1) + m + tul[h] * at;
+            const R di = row[h * BLOCK] + pt0[h] * at + dwc[h] * R(ct[4 + h]);
+            dp[h] = (di + m * dp[h]) * r_rcp(bi - m * cneg[h]);
+            row[h * BLOCK] = r_min(dp[h], y.tmax);
+        }
     }
-    // back substitution on the uncapped solution; the cap applies to what is stored
-    const R tmax = P[U_TMAX];
-    R x = dprev;
-    T[(n - 1) * BLOCK] = r_min(x, tmax);
-    for (int i = n - 2; i >= 0; --i) {
-        x = T[i * BLOCK] - cp[i * BLOCK] * x;
-        T[i * BLOCK] = r_min(x, tmax);
+#pragma unroll 2
+    while (row != col) {
+        row -= UDEB_ROW;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            dp[h] = row[h * BLOCK] + row[(2 + h) * BLOCK] * dp[h];
+            row[h * BLOCK] = r_min(dp[h], y.tmax);
+        }
     }
-    return T[0];
 }
 
 // in: [ERF at_start, ERF at_end, Surface Temperature[4] at_start]
@@ -295,11 +289,11 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
 {
     if (S[US_OK] == R(0)) return false; // from_parameters failed for this member (LAMCALC did not converge)
     const int n = static_cast<int>(P[U_NLAYERS]), steps_n = static_cast<int>(P[U_STEPS]);
-    R *T0 = cx.sm + nr.sm * BLOCK, *T1 = T0 + n * BLOCK, *cp = T0 + 2 * n * BLOCK;
+    R *col = cx.sm + nr.sm * BLOCK; // layer-major {T_nh, T_sh, c'_nh, c'_sh}, see udeb_step_both
     const double *ctab = cx.ctab + nr.ctab;
     const R erf_start = in[0], erf_end = in[1];
-    if (T0[0] == R(0) && in[2] != R(0)) { // warm start from non-zero initial surface temperatures
-        T0[0] = in[2]; T1[0] = in[4];
+    if (col[0] == R(0) && in[2] != R(0)) { // warm start from non-zero initial surface temperatures
+        col[0] = in[2]; col[BLOCK] = in[4];
         S[US_LAND0] = in[3]; S[US_LAND1] = in[5];
         S[US_GR0] = S[US_LAND0]; S[US_GR1] = S[US_LAND1];
     }
@@ -337,29 +331,56 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     const R fgno = area[0], fgnl = area[1], fgso = area[2], fgsl = area[3];
     const bool lhc = P[U_LHC_ON] != R(0);
     const R c_ground = lhc ? udeb_heat_capacity(P[U_LHC_THICK]) : R(0);
-    const R a_nh = S[US_AE0], a_sh = S[US_AE1];
+    UdebYear<R> y;
+    {
+        const R dz = P[U_DZ], dz_mix = P[U_MLD], dz1 = dz / R(2), conv = R(3155.76); // DIFFUSIVITY_CM2S_TO_M2YR
+        const R c_mix = udeb_heat_capacity(dz_mix);
+        y.cA = dt_sub / (dz * dz);
+        y.cA1 = dt_sub / (dz * dz1);
+        y.cM = dt_sub / (dz_mix * dz1);
+        y.dt_mix = dt_sub / dz_mix;
+        y.dtdz = dt_sub / dz;
+        y.dt_cmix = dt_sub / c_mix;
+        y.kc = P[U_KAPPA] * conv;
+        y.kmin = P[U_KAPPA_MIN] * conv;
+        y.dkdt_c = P[U_KAPPA_DKDT] * conv;
+        y.pi_ratio = P[U_PI_RATIO];
+        y.tmax = P[U_TMAX];
+        y.lhc = lhc;
+        for (int h = 0; h < 2; ++h) {
+            const R f_l = (h == 0 ? fgnl : fgsl), f_o = R(0.5) - f_l;
+            const R denominator = f_o * (P[U_KLO] + f_l * lam_l);
+            y.tfb_dt[h] = S[US_AE0 + h] / c_mix * (lam_o + lam_l * P[U_KLO] * P[U_AMP] * f_l / denominator) * dt_sub;
+            y.famp[h] = R(1) + P[U_KLO] * f_l / denominator;
+            y.lhc_c[h] = lhc ? P[U_KLG] / (c_mix * f_o) * dt_sub : R(0);
+        }
+    }
+    const R gr_c0 = (lhc && !(fgnl < R(1e-15))) ? P[U_KLG] / (fgnl * c_ground) * dt_sub : R(0);
+    const R gr_c1 = (lhc && !(fgsl < R(1e-15))) ? P[U_KLG] / (fgsl * c_ground) * dt_sub : R(0);
+    const R inv_steps = R(1) / steps;
+    const R hx_c0 = (fgno > R(1e-15)) ? P[U_KNS] / fgno : R(0), hx_c1 = (fgso > R(1e-15)) ? P[U_KNS] / fgso : R(0);
+    const R w0 = P[U_W0], fv = P[U_WVAR], wmin = w0 * (R(1) - fv);
+    const R inv_wt_nh = R(1) / P[U_WT_NH], inv_wt_sh = R(1) / P[U_WT_SH];
     for (int step = 1; step <= steps_n; ++step) {
-        const R frac = R(step) / steps;
+        const R frac = R(step) * inv_steps;
         const R erf = erf_start + frac * (erf_end - erf_start);
         R forcing[4];
         udeb_apply_efficacy(P, S, erf, co2_eff, forcing);
         if (lhc) {
-            if (!(fgnl < R(1e-15))) S[US_GR0] += P[U_KLG] * (S[US_LAND0] - S[US_GR0]) / (fgnl * c_ground) * dt_sub;
-            if (!(fgsl < R(1e-15))) S[US_GR1] += P[U_KLG] * (S[US_LAND1] - S[US_GR1]) / (fgsl * c_ground) * dt_sub;
+            if (!(fgnl < R(1e-15))) S[US_GR0] += gr_c0 * (S[US_LAND0] - S[US_GR0]);
+            if (!(fgsl < R(1e-15))) S[US_GR1] += gr_c1 * (S[US_LAND1] - S[US_GR1]);
         }
-        const R sst_nh = udeb_step_hemisphere(P, S, ctab, T0, cp, 0, forcing[0], dt_sub, lam_o, lam_l, S[US_HX0], S[US_GR0], a_nh);
-        const R sst_sh = udeb_step_hemisphere(P, S, ctab, T1, cp, 1, forcing[2], dt_sub, lam_o, lam_l, S[US_HX1], S[US_GR1], a_sh);
-        const R air_nho = udeb_sst_to_air(P, sst_nh), air_sho = udeb_sst_to_air(P, sst_sh);
+        udeb_step_both(y, P, S, ctab, n, col, forcing[0], forcing[2]);
+        const R air_nho = udeb_sst_to_air(P, col[0]), air_sho = udeb_sst_to_air(P, col[BLOCK]);
         S[US_LAND0] = udeb_land_temperature(P, air_nho, forcing[1], fgnl, lam_l);
         S[US_LAND1] = udeb_land_temperature(P, air_sho, forcing[3], fgsl, lam_l);
-        if (fgno > R(1e-15)) S[US_HX0] = P[U_KNS] / fgno * (air_sho - air_nho);
-        if (fgso > R(1e-15)) S[US_HX1] = P[U_KNS] / fgso * (air_nho - air_sho);
+        if (fgno > R(1e-15)) S[US_HX0] = hx_c0 * (air_sho - air_nho);
+        if (fgso > R(1e-15)) S[US_HX1] = hx_c1 * (air_nho - air_sho);
         const R gt = air_nho * fgno + S[US_LAND0] * fgnl + air_sho * fgso + S[US_LAND1] * fgsl;
-        const R w0 = P[U_W0], fv = P[U_WVAR], wmin = w0 * (R(1) - fv);
-        S[US_W0] = r_max(w0 * (R(1) - fv * r_min(gt / P[U_WT_NH], R(1))), wmin);
-        S[US_W1] = r_max(w0 * (R(1) - fv * r_min(gt / P[U_WT_SH], R(1))), wmin);
+        S[US_W0] = r_max(w0 * (R(1) - fv * r_min(gt * inv_wt_nh, R(1))), wmin);
+        S[US_W1] = r_max(w0 * (R(1) - fv * r_min(gt * inv_wt_sh, R(1))), wmin);
     }
-    const R sst_nh = T0[0], sst_sh = T1[0];
+    const R sst_nh = col[0], sst_sh = col[BLOCK];
     S[US_AE0] = (r_abs(sst_nh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(P, sst_nh) / sst_nh;
     S[US_AE1] = (r_abs(sst_sh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(P, sst_sh) / sst_sh;
     const R st[4] = {udeb_sst_to_air(P, sst_nh), S[US_LAND0], udeb_sst_to_air(P, sst_sh), S[US_LAND1]};
@@ -378,9 +399,9 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         const R rho_c = R(1026.0) * R(3985.0);
         R total = R(0);
         for (int h = 0; h < 2; ++h) {
-            const R *T = h == 0 ? T0 : T1;
+            const R *T = col + h * BLOCK;
             total += rho_c * P[U_MLD] * T[0];
-            for (int l = 1; l < n; ++l) total += rho_c * P[U_DZ] * T[l * BLOCK];
+            for (int l = 1; l < n; ++l) total += rho_c * P[U_DZ] * T[l * UDEB_ROW];
         }
         out[1] = total / R(2);
     }

@@ -49,7 +49,15 @@ static std::vector<double> udeb_const_table(const std::vector<double> &p, std::s
         t[n + l] = ab / avg;
         t[2 * n + l] = (at - ab) / avg;
     }
+    // The initial profile only enters the variable-upwelling entrainment terms of step_hemisphere
+    // (ocean_column.rs:150-205), always in the same geometry-only combinations, so the table holds those:
+    //   g[0] = (init[1] - Tp) * af_bottom[0];  g[i] = init[i+1]*af_bottom[i] - init[i]*af_top[i] + Tp*af_diff[i];
+    //   g[n-1] = (Tp - init[n-1]) * af_top[n-1]          (Tp = polar sinking temperature = 1, state.rs default)
+    // followed by omr[l] = 1 - depth_l / total_depth, the relative-depth factor of layer_diffusivities (:23-52).
+    t.resize(6 * n, 0.0);
+    const double tp = 1.0;
     for (int h = 0; h < 2; ++h) {
+        std::vector<double> init(n);
         for (int l = 0; l < n; ++l) {
             double v;
             if (p[34] == 2.0) v = (h == 0 ? CMIP5_NH : CMIP5_SH)[l < 50 ? l : 49];
@@ -57,10 +65,21 @@ static std::vector<double> udeb_const_table(const std::vector<double> &p, std::s
                 const double kap = p[3] * 3155.76;
                 v = (l == 0) ? 17.2 : 1.0 + (17.2 - 1.0) * std::exp(-p[6] * ((static_cast<double>(l) - 1.0) * dz + 0.5 * dz) / kap);
             }
-            t[(3 + h) * n + l] = v;
+            init[l] = v;
         }
+        double *g = &t[(3 + h) * n];
+        g[0] = (init[1] - tp) * t[n];
+        for (int i = 1; i < n - 1; ++i) g[i] = init[i + 1] * t[n + i] - init[i] * t[i] + tp * t[2 * n + i];
+        g[n - 1] = (tp - init[n - 1]) * t[n - 1];
     }
-    return t;
+    const double total_depth = mld + (static_cast<double>(n) - 1.0) * dz;
+    for (int l = 0; l < n; ++l) t[5 * n + l] = 1.0 - (mld + static_cast<double>(l) * dz) / total_depth;
+    // device layout: layer-major, per layer {af_top, af_bottom, af_diff, omr, g_nh, g_sh} (climate_udeb.cuh UDEB_CT)
+    std::vector<double> r(6 * n);
+    static const int order[6] = {0, 1, 2, 5, 3, 4};
+    for (int l = 0; l < n; ++l)
+        for (int k = 0; k < 6; ++k) r[6 * l + k] = t[order[k] * n + l];
+    return r;
 }
 
 // OceanCarbon: scaled impulse-response function by lag in months, irf(k/12) for k = 0 .. steps*(T-1)
@@ -185,7 +204,7 @@ static const std::vector<KindInfo> &kinds()
          1, -2,
          // geometry / switches are per-graph (they size the shared-memory layout and the host-computed tables)
          {0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 1},
-         96, /*n_state*/ 19, /*n_smem*/ 150, /*scratch_per_T*/ 1, /*needs_time*/ true,
+         96, /*n_state*/ 19, /*n_smem*/ 200, /*scratch_per_T*/ 1, /*needs_time*/ true,
          /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table},
         {RSCM_B200_FOUR_BOX_OHU, "FourBoxOceanHeatUptake", "four_box_ohu",
          // crates/rscm-components/src/components/four_box_ocean_heat_uptake.rs
@@ -382,8 +401,9 @@ static void emit_program(Graph &g)
     for (const Node &n : g.nodes)
         if (n.kind != KIND_AGGREGATOR) weight += kind_info(n.kind)->reg_weight;
     // 8 CTAs of 128 threads per SM = 64 registers per thread; register-hungry programs get 4 (128 registers)
-    // programs with per-thread shared-memory scratch are limited by shared memory, not registers
-    o << "    static constexpr int MIN_BLOCKS = " << (g.n_smem > 0 ? 1 : (weight <= 32 ? 8 : 4)) << ";\n";
+    // programs with per-thread shared-memory scratch are limited by shared memory, not registers (2 = no register cap;
+    // two CTAs fit one SM in fp32)
+    o << "    static constexpr int MIN_BLOCKS = " << (g.n_smem > 0 ? 2 : (weight <= 32 ? 8 : 4)) << ";\n";
     o << "    static constexpr int NS = " << g.n_state << ";\n";
     o << "    static constexpr int NSM = " << g.n_smem << ";\n";
     o << "    static constexpr bool NEEDS_TIME = " << (g.needs_time ? "true" : "false") << ";\n";

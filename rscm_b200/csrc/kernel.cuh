@@ -198,13 +198,17 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
     double *s_exo = reinterpret_cast<double *>(smem + 16);
-    double *s_obs = s_exo + static_cast<unsigned long long>(a.n_exo_rows) * a.Tpad;
+    // programs with per-thread shared-memory scratch leave the exogenous rows in global memory (block-uniform
+    // broadcast loads that hit L2) so that the scratch of two CTAs fits one SM
+    constexpr bool STAGE_EXO = Prog::NSM == 0;
+    double *s_obs = s_exo + (STAGE_EXO ? static_cast<unsigned long long>(a.n_exo_rows) * a.Tpad : 0ull);
     double *s_bounds = s_obs + static_cast<unsigned long long>(LOGP ? 2 * a.n_obs_rows : 0) * a.Tpad;
     double *s_ctab = s_bounds + (Prog::NEEDS_TIME ? a.Tpad + 4 : 0);
     int *s_nsub = reinterpret_cast<int *>(s_ctab + a.n_ctab);
     R *s_thread = reinterpret_cast<R *>(s_nsub + static_cast<unsigned long long>(a.n_rk) * a.Tpad) + threadIdx.x;
 
-    const unsigned exo_bytes = static_cast<unsigned>(a.n_exo_rows) * a.Tpad * 8u;
+    const unsigned exo_bytes = STAGE_EXO ? static_cast<unsigned>(a.n_exo_rows) * a.Tpad * 8u : 0u;
+    const double *x_exo = STAGE_EXO ? s_exo : a.exo + static_cast<unsigned long long>(blockIdx.y) * a.n_exo_rows * a.Tpad;
     const unsigned obs_bytes = LOGP ? static_cast<unsigned>(2 * a.n_obs_rows) * a.Tpad * 8u : 0u;
     const unsigned bounds_bytes = Prog::NEEDS_TIME ? static_cast<unsigned>(a.Tpad + 4) * 8u : 0u;
     const unsigned ctab_bytes = static_cast<unsigned>(a.n_ctab) * 8u;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
 
 #pragma unroll
     for (int c = 0; c < NC; ++c)
-        if (Prog::exo_row(c) >= 0) cur[c] = static_cast<R>(s_exo[Prog::exo_row(c) * a.Tpad]);
+        if (Prog::exo_row(c) >= 0) cur[c] = static_cast<R>(x_exo[Prog::exo_row(c) * a.Tpad]);
 
     // stateful components: small per-thread state in registers/local (S), large in the per-thread
     // shared-memory scratch and the member-interleaved global scratch (cx.scratch[j*runs + run])
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     for (int N = 0; N < T - 1; ++N) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(s_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
+            if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(x_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
             else nxt[c] = r_nan<R>();
         }
         cx.N = N;

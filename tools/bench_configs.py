@@ -69,14 +69,17 @@ def run_config(name, builder, binds, params, scen, outputs, dtype, sub_stride, y
 
 
 def main():
-    # config 2
-    b, binds, params, scen = syn.config2(M=1 << 20)
-    for dt in ("f64", "f32"):
-        run_config("2: two-layer 1M x 1", b, binds, params, scen, ["Surface Temperature", "Deep Ocean Temperature"], dt, 257)
-    # config 4
-    b, binds, params, scen = syn.config4(M=100_000)
-    for dt in ("f64", "f32"):
-        run_config("4: MAGICC boxes + ClimateUDEB (four-box) 100k", b, binds, params, scen, syn.CONFIG4_OUTPUTS, dt, 499)
+    only = set(sys.argv[1:]) or {"2", "4", "5"}  # e.g. `bench_configs.py 4`
+    if "2" in only:
+        b, binds, params, scen = syn.config2(M=1 << 20)
+        for dt in ("f64", "f32"):
+            run_config("2: two-layer 1M x 1", b, binds, params, scen, ["Surface Temperature", "Deep Ocean Temperature"], dt, 257)
+    if "4" in only:
+        b, binds, params, scen = syn.config4(M=100_000)
+        for dt in ("f64", "f32"):
+            run_config("4: MAGICC boxes + ClimateUDEB (four-box) 100k", b, binds, params, scen, syn.CONFIG4_OUTPUTS, dt, 499)
+    if "5" not in only:
+        return
     # config 5: fused log-posterior
     b, binds, params, scen = syn.config2(M=1 << 20)
     ens = b.build_ensemble().bind_parameters(binds)
