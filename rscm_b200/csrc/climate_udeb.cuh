@@ -9,10 +9,11 @@
 // One thread = one member.  Where the state lives:
 //   * S[20]      (registers): LAMCALC result at the member's base ECS, upwelling rates, land / ground
 //                temperatures, alpha_eff, inter-hemispheric exchange, history length;
-//   * cx.sm      (shared memory, [50][4][BLOCK] per CTA, conflict-free): the two 50-layer ocean columns and
-//                the two Thomas sweeps' c' arrays — the tridiagonal rows are built on the fly, d' overwrites T;
-//   * cx.scratch (global, member-interleaved [T][runs]): the T*dt history of the cumulative-temperature
-//                feedback, summed newest-to-oldest in the reference's order;
+//   * cx.sm      (shared memory, [50][2][BLOCK] per CTA, conflict-free): the two 50-layer ocean columns — the
+//                tridiagonal rows are built on the fly, d' overwrites T (fp32: also the c' columns);
+//   * cx.scratch (global, member-interleaved [100 + T][runs]): the c' columns of the Thomas sweeps (fp64), then
+//                the T*dt history of the cumulative-temperature feedback, summed newest-to-oldest in the
+//                reference's order;
 //   * cx.ctab    (shared memory, per graph): area factors af_top/af_bottom/af_diff, the entrainment
 //                combinations of the initial ocean profile of both hemispheres and the relative-depth factor
 //                of the diffusivity profile — they depend only on geometry parameters, which are
@@ -30,8 +31,8 @@ enum { US_OK, US_LAMO, US_LAML, US_EFF, US_QF0, US_QF1, US_QF2, US_QF3, US_W0, U
        US_AE0, US_AE1, US_HX0, US_HX1, US_NHIST, US_N };
 
 constexpr int UDEB_MAXL = 50;
-constexpr int UDEB_ROW = 4 * BLOCK; // per-thread scratch: values per layer and CTA {T_nh, T_sh, c'_nh, c'_sh}
-constexpr int UDEB_CT = 6;          // constant table: values per layer
+constexpr int UDEB_ROW = 2 * BLOCK; // per-thread shared-memory scratch: values per layer and CTA {T_nh, T_sh}
+constexpr int UDEB_CT = 8;          // constant table: values per layer
 
 // f64::min / f64::max: NaN-ignoring, like fmin / fmax
 __device__ __forceinline__ double r_min(double a, double b) { return fmin(a, b); }
@@ -185,7 +186,7 @@ template <class R> __device__ inline void climate_udeb_init_state(const R *P, co
     S[US_AE0] = S[US_AE1] = P[U_TA_ALPHA];
     S[US_HX0] = S[US_HX1] = R(0);
     S[US_NHIST] = R(0);
-    R *col = cx.sm + nr.sm * BLOCK;
+    R *col = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R)));
     for (int i = 0; i < n; ++i) col[i * UDEB_ROW] = col[i * UDEB_ROW + BLOCK] = R(0);
 }
 
@@ -196,90 +197,153 @@ template <class R> struct UdebYear {
     bool lhc;
 };
 
-// step_hemisphere for both hemispheres at once (they only exchange heat through the previous sub-step's state, so
-// the two Thomas recurrences are independent and interleaving them doubles the instruction-level parallelism).
-// Rows are built on the fly; the forward sweep keeps -c' in the per-thread c' column and d' over T; one
-// reciprocal per row; back substitution on the uncapped solution, the cap applies to what is stored.
-// col = this thread's scratch, layer-major: layer i holds {T_nh, T_sh, c'_nh, c'_sh} at col[(4*i + k) * BLOCK].
-// ctab = per layer {af_top, af_bottom, af_diff, omr, g_nh, g_sh} (graph.cpp udeb_const_table).
+// step_hemisphere for both hemispheres at once, each solved by two-ended elimination.
+//
+// The reference runs thomas_solve top to bottom (linear_algebra.rs:41-79): one 50-long recurrence with a
+// reciprocal in the loop-carried chain, i.e. pure latency for a thread.  The same tridiagonal system is solved here
+// by eliminating from both ends towards the middle ("burn at both ends"): rows 0..k the usual way
+// (x_i = d'_i - c'_i x_{i+1}), rows n-1..k+1 mirrored (x_i = d"_i - a'_i x_{i-1}), a 2x2 solve where they meet,
+// and substitution outwards in both directions.  Same solution up to rounding (the system is strictly diagonally
+// dominant), but with the two hemispheres that makes four independent recurrences per thread instead of one.
+// Rows are built on the fly; -c' (or -a') goes to the per-thread c' column and d' over T; one reciprocal per row; the
+// temperature cap applies to what is stored, the substitution carries the uncapped value (ocean_column.rs:226-238).
+// col  = this thread's ocean columns, layer-major: layer i holds {T_nh, T_sh} at col[(2*i + h) * BLOCK];
+// cp   = this thread's c' columns, layer i at cp[(2*i + h) * cs] (where they live: see climate_udeb_solve).
+// ctab = per layer {af_top, af_bottom, af_diff, omr_i, g_nh, g_sh, omr_{i-1}, 0} (graph.cpp udeb_const_table).
+template <class R> struct UdebRow { R at, ab, ad, om, g[2], omu; };
+
+template <class R> __device__ __forceinline__ UdebRow<R> udeb_row(const double *ct)
+{
+    const double2 c01 = *reinterpret_cast<const double2 *>(ct), c23 = *reinterpret_cast<const double2 *>(ct + 2),
+                  c45 = *reinterpret_cast<const double2 *>(ct + 4); // 64-byte rows: 16-byte aligned
+    UdebRow<R> r;
+    r.at = R(c01.x); r.ab = R(c01.y); r.ad = R(c23.x); r.om = R(c23.y); r.g[0] = R(c45.x); r.g[1] = R(c45.y); r.omu = R(ct[6]);
+    return r;
+}
 
 template <class R>
-__device__ __forceinline__ void udeb_step_both(const UdebYear<R> &y, const R *P, R *S, const double *ctab, int n, R *col, R forcing_nh,
-                                               R forcing_sh)
+__device__ __forceinline__ void udeb_step_both(const UdebYear<R> &y, const R *P, R *S, const double *ctab, int n, R *col, R *cp,
+                                               long long cs, R forcing_nh, R forcing_sh)
 {
     const R forcing[2] = {forcing_nh, forcing_sh};
-    R dkc[2], tul[2], pt0[2], dwc[2], kprev[2], cneg[2], dp[2];
-    const R at0 = R(ctab[0]), ab0 = R(ctab[1]), om0 = R(ctab[3]);
-    R *bottom = col + (n - 1) * UDEB_ROW;
+    R dkc[2], tul[2], pt0[2], dwc[2];
+    R tu[2], cn[2], dpt[2]; // top sweep:    k_{i-1}/(dz dz_up) dt, -c'_{i-1}, d'_{i-1}
+    R tb[2], an[2], dpb[2]; // bottom sweep: k_i/(dz dz) dt,       -a'_{i+1}, d"_{i+1}
+    R *rb = col + (n - 1) * UDEB_ROW;
+    R *pb = cp + (n - 1) * 2 * cs, *pt = cp; // c' columns: layer i, hemisphere h at cp[(2*i + h) * cs]
+    const double *cb = ctab + (n - 1) * UDEB_CT;
+    {
+        const R at0 = R(ctab[0]), ab0 = R(ctab[1]), om0 = R(ctab[3]);
+        const UdebRow<R> c = udeb_row<R>(cb);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const R w = S[US_W0 + h];
+            const R t0 = col[h * BLOCK]; // mixed-layer temperature before the solve (entrainment terms)
+            const R tbot = rb[h * BLOCK];
+            dkc[h] = y.dkdt_c * (t0 - tbot);
+            const R delta_w = w - P[U_W0];
+            const R dwv = (r_abs(delta_w) > R(1e-15)) ? delta_w : R(0);
+            dwc[h] = y.dtdz * dwv;
+            tul[h] = w * y.dtdz;
+            pt0[h] = y.pi_ratio * tul[h] * t0;
+            { // row 0: mixed layer
+                const R k0 = r_max(om0 * dkc[h] + y.kc, y.kmin);
+                const R term_diff = k0 * y.cM, term_upwell = w * y.dt_mix;
+                const R b0 = R(1) + y.tfb_dt[h] * at0 + term_diff * ab0 + term_upwell * y.pi_ratio * ab0;
+                R d0 = t0 + (forcing[h] * y.famp[h] + S[US_HX0 + h]) * y.dt_cmix * at0;
+                if (y.lhc) d0 -= y.lhc_c[h] * (S[US_LAND0 + h] - S[US_GR0 + h]) * at0;
+                d0 += y.dt_mix * dwv * R(ctab[4 + h]);
+                const R r = r_rcp(b0);
+                cn[h] = (term_diff + term_upwell) * ab0 * r;
+                dpt[h] = d0 * r;
+                pt[h * cs] = cn[h];
+                col[h * BLOCK] = dpt[h];
+                tu[h] = k0 * y.cA1; // the layer below the mixed layer sees half a layer thickness upwards
+            }
+            { // row n-1: bottom layer (no diffusion below)
+                const R ku = r_max(c.omu * dkc[h] + y.kc, y.kmin);
+                tb[h] = ku * y.cA;
+                const R m = tb[h] * c.at;
+                const R bi = R(1) + m + tul[h] * c.at;
+                const R di = tbot + pt0[h] * c.at + dwc[h] * c.g[h];
+                const R r = r_rcp(bi);
+                an[h] = m * r;
+                dpb[h] = di * r;
+                pb[h * cs] = an[h];
+                rb[h * BLOCK] = dpb[h];
+            }
+        }
+    }
+    // interior rows 1..n-2: the top sweep takes 1..k, the bottom sweep n-2..k+1 (one more when n is odd)
+    const int k = (n - 2) >> 1;
+    R *rt = col;
+    const double *ctp = ctab;
+    auto bottom_row = [&](R cu) {
+        rb -= UDEB_ROW; cb -= UDEB_CT; pb -= 2 * cs;
+        const UdebRow<R> c = udeb_row<R>(cb);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const R ku = r_max(c.omu * dkc[h] + y.kc, y.kmin);
+            const R m = ku * cu * c.at; // -a_i
+            const R tdd = tb[h];
+            const R bi = R(1) + m + tdd * c.ab + tul[h] * c.at;
+            const R cnum = (tdd + tul[h]) * c.ab; // -c_i
+            const R di = rb[h * BLOCK] + pt0[h] * c.ad + dwc[h] * c.g[h];
+            const R r = r_rcp(bi - cnum * an[h]);
+            an[h] = m * r;
+            dpb[h] = (di + cnum * dpb[h]) * r;
+            pb[h * cs] = an[h];
+            rb[h * BLOCK] = dpb[h];
+            tb[h] = ku * y.cA;
+        }
+    };
+    for (int j = 0; j < k; ++j) {
+        rt += UDEB_ROW; ctp += UDEB_CT; pt += 2 * cs;
+        const UdebRow<R> c = udeb_row<R>(ctp);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const R tdd = r_max(c.om * dkc[h] + y.kc, y.kmin) * y.cA;
+            const R m = tu[h] * c.at; // -a_i
+            const R bi = R(1) + m + tdd * c.ab + tul[h] * c.at;
+            const R cnum = (tdd + tul[h]) * c.ab; // -c_i
+            const R di = rt[h * BLOCK] + pt0[h] * c.ad + dwc[h] * c.g[h];
+            const R r = r_rcp(bi - m * cn[h]);
+            cn[h] = cnum * r;
+            dpt[h] = (di + m * dpt[h]) * r;
+            pt[h * cs] = cn[h];
+            rt[h * BLOCK] = dpt[h];
+            tu[h] = tdd;
+        }
+        bottom_row(y.cA);
+    }
+    if (n & 1) bottom_row(n == 3 ? y.cA1 : y.cA);
+    // rt = row k (top sweep's last), rb = row k+1 (bottom sweep's last): 2x2 solve, then outwards
+    R xu[2], xd[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const R w = S[US_W0 + h];
-        const R t0 = col[h * BLOCK]; // mixed-layer temperature before the solve (entrainment terms)
-        dkc[h] = y.dkdt_c * (t0 - bottom[h * BLOCK]);
-        const R delta_w = w - P[U_W0];
-        const R dwv = (r_abs(delta_w) > R(1e-15)) ? delta_w : R(0);
-        dwc[h] = y.dtdz * dwv;
-        tul[h] = w * y.dtdz;
-        pt0[h] = y.pi_ratio * tul[h] * t0;
-        // row 0: mixed layer
-        const R k0 = r_max(om0 * dkc[h] + y.kc, y.kmin);
-        const R term_diff = k0 * y.cM, term_upwell = w * y.dt_mix;
-        const R b0 = R(1) + y.tfb_dt[h] * at0 + term_diff * ab0 + term_upwell * y.pi_ratio * ab0;
-        R d0 = t0 + (forcing[h] * y.famp[h] + S[US_HX0 + h]) * y.dt_cmix * at0;
-        if (y.lhc) d0 -= y.lhc_c[h] * (S[US_LAND0 + h] - S[US_GR0 + h]) * at0;
-        d0 += y.dt_mix * dwv * R(ctab[4 + h]);
-        const R r = r_rcp(b0);
-        cneg[h] = (term_diff + term_upwell) * ab0 * r;
-        dp[h] = d0 * r;
-        col[(2 + h) * BLOCK] = cneg[h];
-        col[h * BLOCK] = dp[h];
-        kprev[h] = k0;
+        xu[h] = (dpt[h] + cn[h] * dpb[h]) * r_rcp(R(1) - cn[h] * an[h]);
+        xd[h] = dpb[h] + an[h] * xu[h];
+        rt[h * BLOCK] = r_min(xu[h], y.tmax);
+        rb[h * BLOCK] = r_min(xd[h], y.tmax);
     }
-    R cu = y.cA1; // 1/(dz*dz_up): the layer below the mixed layer sees half a layer thickness upwards
-    R *row = col + UDEB_ROW;
-    const double *ct = ctab + UDEB_CT;
-#pragma unroll 2
-    for (; row != bottom; row += UDEB_ROW, ct += UDEB_CT) {
-        const double2 c01 = *reinterpret_cast<const double2 *>(ct), c23 = *reinterpret_cast<const double2 *>(ct + 2),
-                      c45 = *reinterpret_cast<const double2 *>(ct + 4); // 48-byte rows: 16-byte aligned
-        const R at = R(c01.x), ab = R(c01.y), ad = R(c23.x), om = R(c23.y);
-        const R gh[2] = {R(c45.x), R(c45.y)};
+    auto down_row = [&]() {
+        rb += UDEB_ROW; pb += 2 * cs;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const R k_i = r_max(om * dkc[h] + y.kc, y.kmin);
-            const R m = kprev[h] * cu * at; // -a_i
-            const R tdd = k_i * y.cA;
-            const R bi = R(1) + m + tdd * ab + tul[h] * at;
-            const R di = row[h * BLOCK] + pt0[h] * ad + dwc[h] * gh[h];
-            const R r = r_rcp(bi - m * cneg[h]);
-            cneg[h] = (tdd + tul[h]) * ab * r;
-            dp[h] = (di + m * dp[h]) * r;
-            row[(2 + h) * BLOCK] = cneg[h];
-            row[h * BLOCK] = dp[h];
-            kprev[h] = k_i;
+            xd[h] = rb[h * BLOCK] + pb[h * cs] * xd[h];
+            rb[h * BLOCK] = r_min(xd[h], y.tmax);
         }
-        cu = y.cA;
-    }
-    {
-        const R at = R(ct[0]);
+    };
+    for (int j = 0; j < k; ++j) {
+        rt -= UDEB_ROW; pt -= 2 * cs;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const R m = kprev[h] * y.cA * at;
-            const R bi = R(1) + m + tul[h] * at;
-            const R di = row[h * BLOCK] + pt0[h] * at + dwc[h] * R(ct[4 + h]);
-            dp[h] = (di + m * dp[h]) * r_rcp(bi - m * cneg[h]);
-            row[h * BLOCK] = r_min(dp[h], y.tmax);
+            xu[h] = rt[h * BLOCK] + pt[h * cs] * xu[h];
+            rt[h * BLOCK] = r_min(xu[h], y.tmax);
         }
+        down_row();
     }
-#pragma unroll 2
-    while (row != col) {
-        row -= UDEB_ROW;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            dp[h] = row[h * BLOCK] + row[(2 + h) * BLOCK] * dp[h];
-            row[h * BLOCK] = r_min(dp[h], y.tmax);
-        }
-    }
+    if (n & 1) down_row();
 }
 
 // in: [ERF at_start, ERF at_end, Surface Temperature[4] at_start]
@@ -289,7 +353,19 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
 {
     if (S[US_OK] == R(0)) return false; // from_parameters failed for this member (LAMCALC did not converge)
     const int n = static_cast<int>(P[U_NLAYERS]), steps_n = static_cast<int>(P[U_STEPS]);
-    R *col = cx.sm + nr.sm * BLOCK; // layer-major {T_nh, T_sh, c'_nh, c'_sh}, see udeb_step_both
+    R *col = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R))); // layer-major {T_nh, T_sh}, see udeb_step_both
+    // The c' columns of the Thomas sweeps.  The per-thread shared-memory scratch is 100 8-byte words: in fp64 the
+    // ocean columns fill it (two CTAs per SM) and c' goes to this run's rows of the global scratch (coalesced, lives
+    // in L2: written and read back within one sub-step); in fp32 it holds both.
+    R *cp;
+    long long cs;
+    if (sizeof(R) == 8) {
+        cp = reinterpret_cast<R *>(cx.scratch0 + static_cast<long long>(nr.scr) * cx.runs) + cx.run;
+        cs = cx.runs;
+    } else {
+        cp = col + 2 * UDEB_MAXL * BLOCK;
+        cs = BLOCK;
+    }
     const double *ctab = cx.ctab + nr.ctab;
     const R erf_start = in[0], erf_end = in[1];
     if (col[0] == R(0) && in[2] != R(0)) { // warm start from non-zero initial surface temperatures
@@ -309,7 +385,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         for (int i = nhist - 1; i >= 0; --i) {
             if (rem <= R(0)) break;
             const R dt = R(cx.bounds[i + 1] - cx.bounds[i]);
-            const R h = R(cx.scratch[static_cast<long long>(nr.scr + i) * cx.runs]);
+            const R h = R(cx.scratch[static_cast<long long>(nr.scr + 2 * UDEB_MAXL + i) * cx.runs]);
             if (dt <= rem) { sum += h; rem -= dt; }
             else { sum += h * (rem / dt); rem = R(0); }
         }
@@ -370,7 +446,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
             if (!(fgnl < R(1e-15))) S[US_GR0] += gr_c0 * (S[US_LAND0] - S[US_GR0]);
             if (!(fgsl < R(1e-15))) S[US_GR1] += gr_c1 * (S[US_LAND1] - S[US_GR1]);
         }
-        udeb_step_both(y, P, S, ctab, n, col, forcing[0], forcing[2]);
+        udeb_step_both(y, P, S, ctab, n, col, cp, cs, forcing[0], forcing[2]);
         const R air_nho = udeb_sst_to_air(P, col[0]), air_sho = udeb_sst_to_air(P, col[BLOCK]);
         S[US_LAND0] = udeb_land_temperature(P, air_nho, forcing[1], fgnl, lam_l);
         S[US_LAND1] = udeb_land_temperature(P, air_sho, forcing[3], fgsl, lam_l);
@@ -385,7 +461,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     S[US_AE1] = (r_abs(sst_sh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(P, sst_sh) / sst_sh;
     const R st[4] = {udeb_sst_to_air(P, sst_nh), S[US_LAND0], udeb_sst_to_air(P, sst_sh), S[US_LAND1]};
     const R gt = st[0] * fgno + st[1] * fgnl + st[2] * fgso + st[3] * fgsl;
-    cx.scratch[static_cast<long long>(nr.scr + nhist) * cx.runs] = static_cast<double>(gt * dt_year);
+    cx.scratch[static_cast<long long>(nr.scr + 2 * UDEB_MAXL + nhist) * cx.runs] = static_cast<double>(gt * dt_year);
     S[US_NHIST] = R(nhist + 1);
     R f_end[4];
     udeb_apply_efficacy(P, S, erf_end, co2_eff, f_end);

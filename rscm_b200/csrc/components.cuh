@@ -28,7 +28,8 @@ template <class R> struct StepCtx {
     const double *gtab;   // large per-graph constant tables (global memory, read through the read-only path)
     R *sm;                // this thread's shared-memory scratch: element j at sm[j * BLOCK]
     double *scratch;      // this run's global scratch: element j at scratch[j * runs]
-    long long runs;
+    double *scratch0;     // the launch's global scratch (row j of all runs at scratch0 + j * runs)
+    long long runs, run;
     int Tpad;
     int N;                // current time index
 };

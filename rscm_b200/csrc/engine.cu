@@ -176,7 +176,7 @@ size_t smem_bytes(const rscm_b200_ensemble *h, bool logp)
     if (h->g.needs_time) b += static_cast<size_t>(h->Tpad + 4) * 8;
     b += h->g.ctab.size() * 8;
     b += static_cast<size_t>(h->g.n_rk) * h->Tpad * 4;
-    b += static_cast<size_t>(h->g.n_smem) * rscm_dev::BLOCK * (h->dtype ? 4 : 8);
+    b += static_cast<size_t>(h->g.n_smem) * rscm_dev::BLOCK * 8; // n_smem counts 8-byte words per thread in both dtypes
     return b;
 }
 

@@ -74,11 +74,14 @@ static std::vector<double> udeb_const_table(const std::vector<double> &p, std::s
     }
     const double total_depth = mld + (static_cast<double>(n) - 1.0) * dz;
     for (int l = 0; l < n; ++l) t[5 * n + l] = 1.0 - (mld + static_cast<double>(l) * dz) / total_depth;
-    // device layout: layer-major, per layer {af_top, af_bottom, af_diff, omr, g_nh, g_sh} (climate_udeb.cuh UDEB_CT)
-    std::vector<double> r(6 * n);
+    // device layout: layer-major, per layer {af_top, af_bottom, af_diff, omr_l, g_nh, g_sh, omr_{l-1}, 0}
+    // (climate_udeb.cuh UDEB_CT = 8: 64-byte rows, 128-bit shared-memory loads)
+    std::vector<double> r(8 * n, 0.0);
     static const int order[6] = {0, 1, 2, 5, 3, 4};
-    for (int l = 0; l < n; ++l)
-        for (int k = 0; k < 6; ++k) r[6 * l + k] = t[order[k] * n + l];
+    for (int l = 0; l < n; ++l) {
+        for (int k = 0; k < 6; ++k) r[8 * l + k] = t[order[k] * n + l];
+        r[8 * l + 6] = l > 0 ? t[5 * n + l - 1] : 0.0;
+    }
     return r;
 }
 
@@ -204,8 +207,9 @@ static const std::vector<KindInfo> &kinds()
          1, -2,
          // geometry / switches are per-graph (they size the shared-memory layout and the host-computed tables)
          {0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 1},
-         96, /*n_state*/ 19, /*n_smem*/ 200, /*scratch_per_T*/ 1, /*needs_time*/ true,
-         /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table},
+         96, /*n_state*/ 19, /*n_smem*/ 100, /*scratch_per_T*/ 1, /*needs_time*/ true,
+         /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table, nullptr,
+         /*aux_param*/ -1, /*scratch_fixed: c' columns of both hemispheres*/ 100},
         {RSCM_B200_FOUR_BOX_OHU, "FourBoxOceanHeatUptake", "four_box_ohu",
          // crates/rscm-components/src/components/four_box_ocean_heat_uptake.rs
          {{"Effective Radiative Forcing|Aggregated", REQ_INPUT, RSCM_B200_SCALAR}, {"Heat Uptake|Ocean", REQ_OUTPUT, RSCM_B200_FOUR_BOX}},
@@ -777,7 +781,7 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         n.ctab_base = static_cast<int>(g.ctab.size());
         g.n_state += k->n_state;
         g.n_smem += k->n_smem;
-        g.n_scratch_rows += k->scratch_per_T * g.T;
+        g.n_scratch_rows += k->scratch_fixed + k->scratch_per_T * g.T;
         g.needs_time = g.needs_time || k->needs_time;
         if (k->const_table) {
             std::string terr;

@@ -37,7 +37,7 @@ struct KindInfo {
     int reg_weight;            // rough register appetite; decides the kernel's min-CTAs-per-SM hint
     // stateful kinds (ClimateUDEB, ...): sizes of the per-thread state the fused kernel provides
     int n_state = 0;       // register/local values (R S[])
-    int n_smem = 0;        // per-thread shared-memory scratch values
+    int n_smem = 0;        // per-thread shared-memory scratch, in 8-byte words (both compute dtypes)
     int scratch_per_T = 0; // global scratch rows per time point (member-interleaved)
     bool needs_time = false; // solve uses the time bounds
     // input access override: (input index, mode) per `in[]` entry group; mode 0 = get(), 1 = at_start, 2 = at_end.
@@ -48,6 +48,7 @@ struct KindInfo {
     // large per-graph table kept in global memory (n_times is passed for tables sized by the run length)
     std::vector<double> (*global_table)(const std::vector<double> &params, int n_times, std::string &err) = nullptr;
     int aux_param = -1; // index of an integer parameter handed to the device code as a compile-time literal
+    int scratch_fixed = 0; // global scratch rows that do not scale with the run length (come first in the node's rows)
 };
 
 const KindInfo *kind_info(int kind);

@@ -269,11 +269,15 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     cx.gtab = a.gtab;
     cx.sm = s_thread;
     cx.scratch = a.scratch ? a.scratch + run : nullptr;
+    cx.scratch0 = a.scratch;
     cx.runs = a.runs;
+    cx.run = run;
     cx.Tpad = a.Tpad;
     cx.N = 0;
     R S[Prog::NS > 0 ? Prog::NS : 1];
-    Prog::template init_state<R>(P, D, S, cx);
+    // padding threads of the last CTA (clamped to run M-1) must not step: they would race with the real run on its
+    // global scratch rows
+    if (active) Prog::template init_state<R>(P, D, S, cx);
 
     double ll[MAX_OBS_ROWS] = {0.0, 0.0, 0.0, 0.0};
     bool bad = false;
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
             else nxt[c] = r_nan<R>();
         }
         cx.N = N;
-        Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
+        if (active) Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
 
         if (WRITE) {
             if (N + 1 == tnext && tnext < a.t_stop) { // block-uniform
