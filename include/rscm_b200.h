@@ -61,7 +61,12 @@ typedef enum {
     RSCM_B200_TERRESTRIAL_CARBON = 13, /* crates/rscm-magicc/src/parameters/terrestrial_carbon.rs */
     RSCM_B200_CH4_CHEMISTRY = 14,   /* crates/rscm-magicc/src/parameters/ch4_chemistry.rs */
     RSCM_B200_N2O_CHEMISTRY = 15,   /* crates/rscm-magicc/src/parameters/n2o_chemistry.rs */
-    RSCM_B200_OCEAN_CARBON = 16     /* crates/rscm-magicc/src/parameters/ocean_carbon.rs (IRF forms flattened, 60 values) */
+    RSCM_B200_OCEAN_CARBON = 16,    /* crates/rscm-magicc/src/parameters/ocean_carbon.rs (IRF forms flattened, 60 values) */
+    /* crates/rscm-magicc/src/parameters/halocarbon.rs with the reference's default species list (:203-262, 23 F-gases
+     * then 18 Montreal gases): br_multiplier, cfc11_release_normalisation, eesc_delay, air_molar_mass,
+     * atmospheric_mass_tg, mixing_box_fraction, then per species lifetime, radiative_efficiency, concentration_pi,
+     * molecular_weight, n_cl, n_br, fractional_release (293 values; all per-graph, none bindable per member) */
+    RSCM_B200_HALOCARBON_CHEMISTRY = 17
 } rscm_b200_component_kind;
 
 /* GridType — crates/rscm-core/src/component.rs:56-64 */

@@ -20,6 +20,7 @@ TWO_LAYER, CARBON_CYCLE, CO2_ERF, GHG_FORCING = 1, 2, 3, 5
 OZONE_FORCING, AEROSOL_DIRECT, AEROSOL_INDIRECT, CLIMATE_UDEB = 6, 7, 8, 9
 FOUR_BOX_OHU, OCEAN_SURFACE_PP, CO2_BUDGET, TERRESTRIAL_CARBON, CH4_CHEMISTRY, N2O_CHEMISTRY = 10, 11, 12, 13, 14, 15
 OCEAN_CARBON = 16
+HALOCARBON_CHEMISTRY = 17
 SCALAR, FOUR_BOX, HEMISPHERIC = 0, 1, 2
 AGG_SUM, AGG_MEAN, AGG_WEIGHTED = 0, 1, 2
 

@@ -7,11 +7,11 @@
 #include <stddef.h>
 
 #define ORC_MAX_NAME 96
-#define ORC_MAX_DEFS 40
-#define ORC_MAX_PARAMS 256
+#define ORC_MAX_DEFS 96
+#define ORC_MAX_PARAMS 320
 #define ORC_MAX_NODES 48
-#define ORC_MAX_VARS 128
-#define ORC_MAX_EDGES 512
+#define ORC_MAX_VARS 224
+#define ORC_MAX_EDGES 1024
 #define ORC_MAX_CONTRIB 16
 
 typedef struct {
@@ -141,5 +141,6 @@ extern const orc_kind_info orc_kind_aerosol_indirect;
 extern const orc_kind_info orc_kind_climate_udeb;
 extern const orc_kind_info orc_kind_fbohu, orc_kind_ospp, orc_kind_co2_budget, orc_kind_terrestrial, orc_kind_ch4, orc_kind_n2o;
 extern const orc_kind_info orc_kind_ocean_carbon;
+const orc_kind_info *orc_kind_halocarbon(void); /* defs are generated from the species list: magicc_halocarbon.c */
 
 #endif

@@ -339,6 +339,7 @@ const orc_kind_info *orc_kind_lookup(int kind)
     case ORC_CH4_CHEMISTRY: return &orc_kind_ch4;
     case ORC_N2O_CHEMISTRY: return &orc_kind_n2o;
     case ORC_OCEAN_CARBON: return &orc_kind_ocean_carbon;
+    case ORC_HALOCARBON_CHEMISTRY: return orc_kind_halocarbon();
     default: return NULL;
     }
 }

@@ -66,6 +66,7 @@ enum {
     ORC_CH4_CHEMISTRY = 14,
     ORC_N2O_CHEMISTRY = 15,
     ORC_OCEAN_CARBON = 16, /* see magicc_ocean.c */
+    ORC_HALOCARBON_CHEMISTRY = 17, /* see magicc_halocarbon.c */
     ORC_KIND_MAX = 32
 };
 

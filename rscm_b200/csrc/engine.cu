@@ -171,7 +171,7 @@ void harvest_event(rscm_b200_ensemble *h, size_t i)
 size_t smem_bytes(const rscm_b200_ensemble *h, bool logp)
 {
     size_t b = 16;
-    if (h->g.n_smem == 0) b += static_cast<size_t>(h->g.n_exo_rows) * h->Tpad * 8; // kernel.cuh STAGE_EXO
+    if (h->g.stage_exo) b += static_cast<size_t>(h->g.n_exo_rows) * h->Tpad * 8; // Prog::STAGE_EXO
     if (logp) b += static_cast<size_t>(2 * h->n_obs_rows) * h->Tpad * 8;
     if (h->g.needs_time) b += static_cast<size_t>(h->Tpad + 4) * 8;
     b += h->g.ctab.size() * 8;

@@ -117,9 +117,79 @@ static std::vector<double> ocean_irf_table(const std::vector<double> &p, int n_t
     return tab;
 }
 
+// HalocarbonChemistry (crates/rscm-magicc/src/chemistry/halocarbon.rs): the reference's default species list
+// (parameters/halocarbon.rs:203-262: 23 F-gases, then 18 Montreal gases).  All parameters are per-graph; the device
+// code reads a per-species table {lifetime, conv*lifetime, radiative_efficiency/1000, concentration_pi,
+// eesc weight = (n_cl + br_multiplier*n_br) * fractional_release/cfc11_release_normalisation (0 when the species
+// releases nothing), is_fgas}.
+static const char *const kHaloSpecies[41] = {
+    "CF4", "C2F6", "C3F8", "C4F10", "C5F12", "C6F14", "C7F16", "C8F18", "c-C4F8", "HFC-23", "HFC-32", "HFC-43-10mee", "HFC-125",
+    "HFC-134a", "HFC-143a", "HFC-152a", "HFC-227ea", "HFC-236fa", "HFC-245fa", "HFC-365mfc", "NF3", "SF6", "SO2F2",
+    "CFC-11", "CFC-12", "CFC-113", "CFC-114", "CFC-115", "HCFC-22", "HCFC-141b", "HCFC-142b", "CH3CCl3", "CCl4", "CH3Cl", "CH2Cl2",
+    "CHCl3", "CH3Br", "Halon-1211", "Halon-1301", "Halon-2402", "Halon-1202"};
+constexpr int kHaloNS = 41, kHaloNF = 23, kHaloNG = 6;
+
+static std::vector<double> halocarbon_const_table(const std::vector<double> &p, std::string &err)
+{
+    std::vector<double> t(6 * kHaloNS, 0.0);
+    const double atm_mass_g = p[4] * 1e12;
+    for (int s = 0; s < kHaloNS; ++s) {
+        const double *sp = &p[kHaloNG + 7 * s];
+        if (!(sp[0] > 0.0) || !(sp[3] > 0.0)) { err = std::string("HalocarbonChemistry: lifetime and molecular_weight of ") + kHaloSpecies[s] + " must be positive"; return {}; }
+        const double conv = (p[3] / sp[3]) * (1e9 / atm_mass_g) * 1e12 / p[5]; // emission_to_concentration_factor :162-172
+        t[6 * s + 0] = sp[0];
+        t[6 * s + 1] = conv;
+        t[6 * s + 2] = sp[1];
+        t[6 * s + 3] = sp[2];
+        t[6 * s + 4] = sp[6] > 0.0 ? sp[4] + p[0] * sp[5] : 0.0; // halogen loading, only for species that release (:211)
+        t[6 * s + 5] = sp[6] > 0.0 ? sp[6] / p[1] : 0.0;           // normalised release
+    }
+    return t;
+}
+
+static KindInfo halocarbon_kind()
+{
+    static std::vector<std::string> names; // storage behind the const char* of the descriptor
+    names.reserve(2 * kHaloNS + 7 * kHaloNS);
+    KindInfo k{};
+    k.kind = RSCM_B200_HALOCARBON_CHEMISTRY;
+    k.type_name = "HalocarbonChemistry";
+    k.dev_name = "halocarbon_chemistry";
+    // definitions() is hand-written in the reference (halocarbon.rs:259-293): emissions input + concentration state
+    // per species, then the four outputs
+    for (int s = 0; s < kHaloNS; ++s) {
+        names.push_back(std::string("Emissions|") + kHaloSpecies[s]);
+        k.defs.push_back({names.back().c_str(), REQ_INPUT, RSCM_B200_SCALAR});
+        names.push_back(std::string("Atmospheric Concentration|") + kHaloSpecies[s]);
+        k.defs.push_back({names.back().c_str(), REQ_STATE, RSCM_B200_SCALAR});
+    }
+    k.defs.push_back({"Forcing|Halocarbons", REQ_OUTPUT, RSCM_B200_SCALAR});
+    k.defs.push_back({"Forcing|F-gases", REQ_OUTPUT, RSCM_B200_SCALAR});
+    k.defs.push_back({"Forcing|Montreal Gases", REQ_OUTPUT, RSCM_B200_SCALAR});
+    k.defs.push_back({"EESC", REQ_OUTPUT, RSCM_B200_SCALAR});
+    k.param_names = {"br_multiplier", "cfc11_release_normalisation", "eesc_delay", "air_molar_mass", "atmospheric_mass_tg", "mixing_box_fraction"};
+    static const char *const fields[7] = {"lifetime", "radiative_efficiency", "concentration_pi", "molecular_weight", "n_cl", "n_br", "fractional_release"};
+    for (int s = 0; s < kHaloNS; ++s)
+        for (int f = 0; f < 7; ++f) {
+            names.push_back(std::string(fields[f]) + "[" + kHaloSpecies[s] + "]");
+            k.param_names.push_back(names.back().c_str());
+        }
+    k.n_derived = 0;
+    k.rk_step_param = -2;
+    k.bindable.assign(k.param_names.size(), 0);
+    k.reg_weight = 48;
+    k.n_state = kHaloNS; // last non-NaN concentration per species (Timeseries::latest_value)
+    k.needs_time = true;
+    // every input through InputState::get_global (mode 3)
+    for (int i = 0; i < 2 * kHaloNS; ++i) k.in_access.push_back({i, 3});
+    k.const_table = &halocarbon_const_table;
+    k.no_slots = true;
+    return k;
+}
+
 static const std::vector<KindInfo> &kinds()
 {
-    static const std::vector<KindInfo> k = {
+    static std::vector<KindInfo> k = {
         {RSCM_B200_TWO_LAYER, "TwoLayer", "two_layer",
          // crates/rscm-two-layer/src/component.rs:147-154
          {{"Effective Radiative Forcing", REQ_INPUT, RSCM_B200_SCALAR},
@@ -295,6 +365,8 @@ static const std::vector<KindInfo> &kinds()
           1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0},
          48, /*n_state*/ 1, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10},
     };
+    static const bool extended = (k.push_back(halocarbon_kind()), true);
+    (void)extended;
     return k;
 }
 
@@ -411,6 +483,9 @@ static void emit_program(Graph &g)
     o << "    static constexpr int NS = " << g.n_state << ";\n";
     o << "    static constexpr int NSM = " << g.n_smem << ";\n";
     o << "    static constexpr bool NEEDS_TIME = " << (g.needs_time ? "true" : "false") << ";\n";
+    // exogenous rows are staged into shared memory unless per-thread scratch or a long row list needs the space
+    g.stage_exo = g.n_smem == 0 && g.n_exo_rows <= 24;
+    o << "    static constexpr bool STAGE_EXO = " << (g.stage_exo ? "true" : "false") << ";\n";
     o << "    __host__ __device__ static constexpr int exo_row(int c) { return ";
     for (int c = 0; c < g.n_cells; ++c) {
         const Variable &v = g.vars[g.cell_var[c]];
@@ -493,6 +568,19 @@ static void emit_program(Graph &g)
                 const int i = ac.first;
                 const int Rc = grid_regions(n.in_grid[i]);
                 const bool at_end = ac.second == 2 || (ac.second == 0 && n.in_src[i] == RSCM_B200_SRC_UPSTREAM);
+                if (ac.second == 3 && n.in_src[i] == RSCM_B200_SRC_UPSTREAM) {
+                    // InputState::get_global of an endogenous series = Timeseries::latest_value (state/mod.rs:231-254):
+                    // the value written this step if it is not NaN, else the one at the current index.  (Own states
+                    // keep their last non-NaN value in the component's S[]; exogenous series are read at the
+                    // current time, NaN included.)
+                    for (int r = 0; r < Rc; ++r) {
+                        const std::string e = input_expr(g, n, i, r, true, pre, tmp_id), b = input_expr(g, n, i, r, false, pre, tmp_id);
+                        const int id = tmp_id++;
+                        pre << "        const R lv" << id << " = " << e << ";\n";
+                        in_exprs.push_back("(lv" + std::to_string(id) + " == lv" + std::to_string(id) + " ? lv" + std::to_string(id) + " : " + b + ")");
+                    }
+                    continue;
+                }
                 for (int r = 0; r < Rc; ++r) in_exprs.push_back(input_expr(g, n, i, r, at_end, pre, tmp_id));
             }
             int n_out_vals = 0;
@@ -768,11 +856,13 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         const KindInfo *k = kind_info(n.kind);
         n.param_base = g.n_slots;
         n.derived_base = g.n_derived;
-        for (size_t p = 0; p < n.params.size(); ++p) {
-            g.slot_default.push_back(n.params[p]);
-            g.slot_bindable.push_back(k->bindable[p]);
+        if (!k->no_slots) {
+            for (size_t p = 0; p < n.params.size(); ++p) {
+                g.slot_default.push_back(n.params[p]);
+                g.slot_bindable.push_back(k->bindable[p]);
+            }
+            g.n_slots += static_cast<int>(n.params.size());
         }
-        g.n_slots += static_cast<int>(n.params.size());
         g.n_derived += k->n_derived;
         // stateful kinds: per-thread state, shared-memory scratch, global scratch, per-graph constant tables
         n.state_base = g.n_state;
@@ -840,6 +930,7 @@ int Graph::resolve_slot(const std::string &slot, std::string &err) const
         const KindInfo *k = kind_info(n.kind);
         if (type != k->type_name) continue;
         if (want_index >= 0 && want_index != ni) continue;
+        if (k->no_slots) { err = "parameters of " + type + " are per-graph and cannot vary per member"; return -1000000000; }
         for (size_t p = 0; p < k->param_names.size(); ++p) {
             if (field != k->param_names[p]) continue;
             if (!slot_bindable[n.param_base + p]) { err = "parameter '" + slot + "' cannot vary per member"; return -1000000000; }

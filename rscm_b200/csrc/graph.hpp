@@ -49,6 +49,7 @@ struct KindInfo {
     std::vector<double> (*global_table)(const std::vector<double> &params, int n_times, std::string &err) = nullptr;
     int aux_param = -1; // index of an integer parameter handed to the device code as a compile-time literal
     int scratch_fixed = 0; // global scratch rows that do not scale with the run length (come first in the node's rows)
+    bool no_slots = false; // all parameters are per-graph and only feed const_table: they take no kernel parameter slots
 };
 
 const KindInfo *kind_info(int kind);
@@ -92,6 +93,7 @@ struct Graph {
     std::vector<int> order;     // node ids in execution order
     std::vector<int> exo_vars;  // variable ids, scenario order
     int n_cells = 0, n_slots = 0, n_derived = 0, n_exo_rows = 0, n_rk = 0;
+    bool stage_exo = true; // Prog::STAGE_EXO: exogenous rows staged in shared memory (else read from global)
     int n_state = 0, n_smem = 0, n_scratch_rows = 0; // stateful components: totals (scratch rows already x T)
     bool needs_time = false;
     std::vector<double> ctab; // concatenated per-graph constant tables (even length)

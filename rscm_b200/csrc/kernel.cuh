@@ -24,8 +24,8 @@
 
 namespace rscm_dev {
 
-constexpr int MAX_SLOTS = 224;  // component parameter slots per program (KArgs stays below the 4 KB parameter limit)
-constexpr int MAX_CELLS = 48;   // scalar storage cells (variables x regions)
+constexpr int MAX_SLOTS = 224;  // component parameter slots per program
+constexpr int MAX_CELLS = 160;  // scalar storage cells (variables x regions); HalocarbonChemistry alone brings 86
 constexpr int MAX_OBS_ROWS = 4; // dense observation tables (one per observed variable)
 
 struct PriorDev {
@@ -86,7 +86,7 @@ struct KArgs {
     long long out_off[MAX_CELLS]; // byte offset of the cell's first output row (row * runs * 8) or -1
 };
 
-static_assert(sizeof(KArgs) <= 4096, "kernel parameter block must stay within the 4 KB launch limit");
+static_assert(sizeof(KArgs) <= 32764, "kernel parameter block must stay within the launch limit (32764 B since CUDA 12.1, sm_70+)");
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) -----------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p)
@@ -198,9 +198,9 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
     double *s_exo = reinterpret_cast<double *>(smem + 16);
-    // programs with per-thread shared-memory scratch leave the exogenous rows in global memory (block-uniform
-    // broadcast loads that hit L2) so that the scratch of two CTAs fits one SM
-    constexpr bool STAGE_EXO = Prog::NSM == 0;
+    // programs with per-thread shared-memory scratch (so that the scratch of two CTAs fits one SM) or with very many
+    // exogenous rows leave them in global memory: block-uniform broadcast loads that hit L1/L2
+    constexpr bool STAGE_EXO = Prog::STAGE_EXO;
     double *s_obs = s_exo + (STAGE_EXO ? static_cast<unsigned long long>(a.n_exo_rows) * a.Tpad : 0ull);
     double *s_bounds = s_obs + static_cast<unsigned long long>(LOGP ? 2 * a.n_obs_rows : 0) * a.Tpad;
     double *s_ctab = s_bounds + (Prog::NEEDS_TIME ? a.Tpad + 4 : 0);

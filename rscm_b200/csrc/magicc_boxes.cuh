@@ -248,4 +248,55 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     return true;
 }
 
+// ---- HalocarbonChemistry — crates/rscm-magicc/src/chemistry/halocarbon.rs -------------------------------------------
+// decay_species :115-134, species_forcing :137-145, calculate_{total,fgas,montreal}_forcing :148-196, calculate_eesc
+// :204-225, solve :295-352.  41 species (the reference's default list), all parameters per-graph: the per-species
+// table {lifetime, conv, radiative_efficiency, concentration_pi, halogen loading, normalised release} comes from
+// the host (graph.cpp halocarbon_const_table) through shared memory.
+// in:  per species [emissions, concentration] as InputState::get_global returns them; out: 41 concentrations,
+// Forcing|Halocarbons, Forcing|F-gases, Forcing|Montreal Gases, EESC.
+// S[s] = the species' last non-NaN concentration: get_global on an endogenous series is Timeseries::latest_value
+// (state/mod.rs:231-254), so a NaN written by one step (NaN emissions) does not stick.
+constexpr int HALO_NS = 41, HALO_NF = 23, HALO_CT = 6;
+constexpr int HALOCARBON_CHEMISTRY_NP = 0;
+constexpr int HALOCARBON_CHEMISTRY_ND = 0;
+
+template <class R> __device__ __forceinline__ void halocarbon_chemistry_prepare(const R *, R *) {}
+
+template <class R> __device__ inline void halocarbon_chemistry_init_state(const R *, const R *, R *S, const StepCtx<R> &, NodeRef)
+{
+#pragma unroll
+    for (int s = 0; s < HALO_NS; ++s) S[s] = r_nan<R>();
+}
+
+template <class R>
+__device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R *in, R *out, const StepCtx<R> &cx, R *S, NodeRef nr)
+{
+    const double *tab = cx.ctab + nr.ctab;
+    const R dt = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
+    R total = R(0), fgas = R(0), montreal = R(0), eesc = R(0);
+#pragma unroll
+    for (int s = 0; s < HALO_NS; ++s) {
+        const double *t = tab + HALO_CT * s;
+        const R lifetime = R(t[0]), conv = R(t[1]), rad_eff = R(t[2]), conc_pi = R(t[3]), loading = R(t[4]), release = R(t[5]);
+        R conc = in[2 * s + 1];
+        if (conc != conc) conc = S[s]; // latest_value: fall back to the last non-NaN value (NaN if there never was one)
+        S[s] = conc;
+        const R decay = r_exp<R>(-dt / lifetime);
+        const R emissions_ppt = in[2 * s] * conv;
+        const R new_conc = conc * decay + emissions_ppt * lifetime * (R(1) - decay);
+        out[s] = new_conc;
+        const R forcing = (new_conc - conc_pi) * rad_eff / R(1000);
+        total += forcing;
+        if (s < HALO_NF) fgas += forcing;
+        else montreal += forcing;
+        if (release > R(0)) eesc += new_conc * loading * release;
+    }
+    out[HALO_NS] = total;
+    out[HALO_NS + 1] = fgas;
+    out[HALO_NS + 2] = montreal;
+    out[HALO_NS + 3] = eesc;
+    return true;
+}
+
 } // namespace rscm_dev

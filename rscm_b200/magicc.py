@@ -257,3 +257,70 @@ class ClimateUDEBBuilder(_ArrayFieldsBuilder):
         if name == "ocean_temp_profile" and isinstance(v, str):
             return {"analytical": 1.0, "cmip5": 2.0, "1": 1.0, "2": 2.0}[v.lower()]
         return float(v)
+
+
+class HalocarbonChemistryBuilder:
+    """HalocarbonParameters — crates/rscm-magicc/src/parameters/halocarbon.rs:104-200, default species tables :203-262.
+
+    ``from_parameters({...})`` takes the reference's scalar fields and, optionally, ``fgases`` / ``montreal_gases`` as lists of the
+    reference's species dicts (``name, lifetime, radiative_efficiency, concentration_pi, molecular_weight, n_cl, n_br,
+    fractional_release``).  The device program is built for the reference's default species *list* (the variable names are part of the
+    compiled graph); the species' *numbers* may be overridden, a different list is refused."""
+
+    TYPE_NAME = "HalocarbonChemistry"
+    SCALARS = (("br_multiplier", 60.0), ("cfc11_release_normalisation", 0.47), ("eesc_delay", 3.0), ("air_molar_mass", 28.97),
+               ("atmospheric_mass_tg", 5.133e9), ("mixing_box_fraction", 0.949))
+    SPECIES_FIELDS = ("lifetime", "radiative_efficiency", "concentration_pi", "molecular_weight", "n_cl", "n_br", "fractional_release")
+    # name, lifetime (yr), radiative efficiency (W/m^2/ppb), pre-industrial (ppt), molecular weight, n_cl, n_br, fractional release
+    FGASES = (
+        ("CF4", 50000.0, 0.09, 0.0, 88.0, 0, 0, 0.0), ("C2F6", 10000.0, 0.25, 0.0, 138.0, 0, 0, 0.0), ("C3F8", 2600.0, 0.28, 0.0, 188.0, 0, 0, 0.0),
+        ("C4F10", 2600.0, 0.36, 0.0, 238.0, 0, 0, 0.0), ("C5F12", 4100.0, 0.41, 0.0, 288.0, 0, 0, 0.0), ("C6F14", 3100.0, 0.44, 0.0, 338.0, 0, 0, 0.0),
+        ("C7F16", 3000.0, 0.50, 0.0, 388.0, 0, 0, 0.0), ("C8F18", 3000.0, 0.55, 0.0, 438.0, 0, 0, 0.0), ("c-C4F8", 3200.0, 0.32, 0.0, 200.0, 0, 0, 0.0),
+        ("HFC-23", 228.0, 0.18, 0.0, 70.0, 0, 0, 0.0), ("HFC-32", 5.4, 0.11, 0.0, 52.0, 0, 0, 0.0), ("HFC-43-10mee", 17.0, 0.359, 0.0, 252.0, 0, 0, 0.0),
+        ("HFC-125", 31.0, 0.23, 0.0, 120.0, 0, 0, 0.0), ("HFC-134a", 14.0, 0.16, 0.0, 102.0, 0, 0, 0.0), ("HFC-143a", 51.0, 0.16, 0.0, 84.0, 0, 0, 0.0),
+        ("HFC-152a", 1.6, 0.10, 0.0, 66.0, 0, 0, 0.0), ("HFC-227ea", 36.0, 0.26, 0.0, 170.0, 0, 0, 0.0), ("HFC-236fa", 213.0, 0.24, 0.0, 152.0, 0, 0, 0.0),
+        ("HFC-245fa", 7.9, 0.24, 0.0, 134.0, 0, 0, 0.0), ("HFC-365mfc", 8.9, 0.22, 0.0, 148.0, 0, 0, 0.0), ("NF3", 569.0, 0.20, 0.0, 71.0, 0, 0, 0.0),
+        ("SF6", 850.0, 0.57, 0.0, 146.0, 0, 0, 0.0), ("SO2F2", 36.0, 0.20, 0.0, 102.0, 0, 0, 0.0),
+    )
+    MONTREAL_GASES = (
+        ("CFC-11", 52.0, 0.295, 0.0, 137.4, 3, 0, 0.47), ("CFC-12", 102.0, 0.364, 0.0, 120.9, 2, 0, 0.23), ("CFC-113", 93.0, 0.30, 0.0, 187.4, 3, 0, 0.29),
+        ("CFC-114", 189.0, 0.31, 0.0, 170.9, 2, 0, 0.12), ("CFC-115", 540.0, 0.20, 0.0, 154.5, 1, 0, 0.04), ("HCFC-22", 11.9, 0.21, 0.0, 86.5, 1, 0, 0.13),
+        ("HCFC-141b", 9.4, 0.16, 0.0, 116.9, 2, 0, 0.34), ("HCFC-142b", 18.0, 0.19, 0.0, 100.5, 1, 0, 0.17), ("CH3CCl3", 5.0, 0.07, 0.0, 133.4, 3, 0, 0.67),
+        ("CCl4", 32.0, 0.174, 0.0, 153.8, 4, 0, 0.56), ("CH3Cl", 0.9, 0.004, 500.0, 50.5, 1, 0, 0.44), ("CH2Cl2", 0.5, 0.028, 0.0, 84.9, 2, 0, 0.0),
+        ("CHCl3", 0.5, 0.07, 0.0, 119.4, 3, 0, 0.0), ("CH3Br", 0.8, 0.004, 5.0, 94.9, 0, 1, 0.60), ("Halon-1211", 16.0, 0.29, 0.0, 165.4, 1, 1, 0.62),
+        ("Halon-1301", 72.0, 0.30, 0.0, 148.9, 0, 1, 0.28), ("Halon-2402", 28.0, 0.31, 0.0, 259.8, 0, 2, 0.65), ("Halon-1202", 2.5, 0.27, 0.0, 209.8, 0, 2, 0.62),
+    )
+
+    def __init__(self, parameters: dict):
+        self._parameters = dict(parameters)
+
+    @classmethod
+    def species_names(cls):
+        return [s[0] for s in cls.FGASES + cls.MONTREAL_GASES]
+
+    @classmethod
+    def from_parameters(cls, parameters: dict):
+        known = {n for n, _ in cls.SCALARS} | {"fgases", "montreal_gases"}
+        unknown = set(parameters) - known
+        if unknown:
+            raise ValueError(f"HalocarbonChemistry: unknown parameter(s) {sorted(unknown)}")
+        return cls(parameters)
+
+    def _species(self, key, defaults):
+        given = self._parameters.get(key)
+        if given is None:
+            return [list(s[1:]) for s in defaults]
+        if [g["name"] for g in given] != [s[0] for s in defaults]:
+            raise ValueError(f"HalocarbonChemistry: the device program is built for the reference's default {key} list "
+                             f"({', '.join(s[0] for s in defaults)}); only the species' numbers may change")
+        return [[float(g[f]) for f in self.SPECIES_FIELDS] for g in given]
+
+    def build(self) -> Component:
+        names = [n for n, _ in self.SCALARS]
+        vals = [float(self._parameters.get(n, d)) for n, d in self.SCALARS]
+        rows = self._species("fgases", self.FGASES) + self._species("montreal_gases", self.MONTREAL_GASES)
+        for sname, row in zip(self.species_names(), rows):
+            names += [f"{f}[{sname}]" for f in self.SPECIES_FIELDS]
+            vals += [float(v) for v in row]
+        assert len(vals) == 293
+        return Component(_ffi.HALOCARBON_CHEMISTRY, self.TYPE_NAME, names, vals)

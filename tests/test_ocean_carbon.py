@@ -92,10 +92,19 @@ def test_ocean_carbon_gpu_parity(model, tmp_path, monkeypatch):
         assert rel_err(got[n], ref[n]) <= 1e-9, n
 
 
-def full_magicc_builder(start=1850, end=1950):
+def full_magicc_builder(start=1850, end=1950, halocarbons=False):
     """Emissions-driven MAGICC: CH4/N2O chemistry, terrestrial + ocean carbon, CO2 budget, GHG / ozone / aerosol forcing,
-    Sum aggregate (with an initial value), ClimateUDEB on the four-box grid."""
+    Sum aggregate (with an initial value), ClimateUDEB on the four-box grid.  ``halocarbons=True`` wires HalocarbonChemistry in:
+    its EESC replaces the exogenous one and Forcing|Halocarbons joins the ERF aggregate."""
+    from rscm_b200.magicc import HalocarbonChemistryBuilder
+    species = HalocarbonChemistryBuilder.species_names() if halocarbons else []
+    erf_parts = list(syn.CONFIG4_ERF_PARTS) + (["Forcing|Halocarbons"] if halocarbons else [])
     schema = VariableSchema()
+    for s in species:
+        schema.add_variable(f"Emissions|{s}", "kt/yr")
+        schema.add_variable(f"Atmospheric Concentration|{s}", "ppt")
+    for n in (("Forcing|Halocarbons", "Forcing|F-gases", "Forcing|Montreal Gases") if halocarbons else ()):
+        schema.add_variable(n, "W/m^2")
     for n in ("CH4", "N2O", "NOx", "CO", "NMVOC", "SOx", "BC", "OC", "CO2|Fossil", "CO2|Land Use"):
         schema.add_variable(f"Emissions|{n}", "")
     schema.add_variable("EESC", "ppt")
@@ -108,9 +117,13 @@ def full_magicc_builder(start=1850, end=1950):
               "Carbon Pool|Detritus", "Carbon Pool|Soil", "Carbon Pool|Humus", "Ocean Surface pCO2", "Cumulative Ocean Uptake",
               "Emissions|CO2|Net", "Airborne Fraction|CO2", "Lifetime|CH4", "Lifetime|N2O"):
         schema.add_variable(n, "")
-    schema.add_aggregate("Effective Radiative Forcing", "W/m^2", "Sum", syn.CONFIG4_ERF_PARTS)
+    schema.add_aggregate("Effective Radiative Forcing", "W/m^2", "Sum", erf_parts)
+    b = ModelBuilder().with_time_axis(syn.time_axis(start, end)).with_schema(schema)
+    if halocarbons:
+        b = (b.with_rust_component(HalocarbonChemistryBuilder.from_parameters({}).build())
+             .with_initial_values({f"Atmospheric Concentration|{s}": (500.0 if s == "CH3Cl" else 5.0 if s == "CH3Br" else 0.0) for s in species}))
     return (
-        ModelBuilder().with_time_axis(syn.time_axis(start, end)).with_schema(schema)
+        b
         .with_rust_component(CH4ChemistryBuilder.from_parameters({}).build())
         .with_rust_component(N2OChemistryBuilder.from_parameters({}).build())
         .with_rust_component(TerrestrialCarbonBuilder.from_parameters({}).build())
