@@ -61,8 +61,16 @@ def run_config(name, builder, binds, params, scen, outputs, dtype, sub_stride, y
     cpu_s = time.perf_counter() - t0
     got, want = ens.split_outputs(sub), m.split(ref, outputs)
     errs = {n: rel_err(got[n], want[n]) for n in outputs}
+    # per-run view of the same comparison: max |gpu - cpu| over the run's series / max |cpu| over it
+    per_run = np.zeros(sub.shape[-1])
+    for n in outputs:
+        a, e = got[n].reshape(-1, sub.shape[-1]), want[n].reshape(-1, sub.shape[-1])
+        with np.errstate(invalid="ignore"):
+            per_run = np.maximum(per_run, np.nanmax(np.abs(a - e), axis=0) / np.maximum(np.nanmax(np.abs(e), axis=0), 1e-300))
     line = {"config": name, "dtype": dtype, "members": M, "scenarios": S, "ms": ms, "member_years_per_s": M * S * years / (ms * 1e-3),
             "jit": ens.program_is_jit(), "parity_subsample": int(idx.size * S), "max_rel_err": max(errs.values()), "rel_err": errs,
+            "per_run_rel_err": {"median": float(np.median(per_run)), "p99": float(np.percentile(per_run, 99)), "max": float(per_run.max()),
+                                "frac_within_1e-4": float(np.mean(per_run <= 1e-4)), "frac_within_1e-9": float(np.mean(per_run <= 1e-9))},
             "cpu_oracle_member_years_per_s": idx.size * S * years / cpu_s, "cpu_threads": orc.max_threads()}
     print(json.dumps(line), flush=True)
     return ens
