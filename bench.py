@@ -52,15 +52,40 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks + throttle reasons polled DURING the timed region (B200_PROFILING.md recipe).  NVML in a thread every
+    ~5 ms (the timed region is ~150 ms: `nvidia-smi -lms 100` would see one sample); nvidia-smi as the fallback."""
 
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.proc = None
-        self.lines = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.proc, self.nvml, self._stop = None, None, threading.Event()
         try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map torch's device through its UUID (CUDA_VISIBLE_DEVICES may reorder)
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            self.handle = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(h)
+                if uuid in (u.decode() if isinstance(u, bytes) else u):
+                    self.handle = h
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.source = "nvidia-smi"
+            self.lines = []
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -68,33 +93,50 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    self.sm.append(float(f[0])); self.mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def measured_peaks():
@@ -247,11 +289,14 @@ def run_ours(args):
         per_launch_my = runs * YEARS
         achieved_tf = FLOP_PER_MEMBER_YEAR * per_launch_my / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else None
         achieved_gbs = BYTES_PER_MEMBER_YEAR * per_launch_my / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
-        traffic = None
+        traffic, ncu_pipe = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp))["dram_bytes_per_member_year"] * per_launch_my
+                prof = json.load(open(tp))
+                traffic = prof["dram_bytes_per_member_year"] * per_launch_my
+                ncu_pipe = {"fp64_pipe_active": prof.get("ncu_fp64_pipe_active"), "issue_active": prof.get("ncu_issue_active"),
+                            "source": prof.get("source")}
             except Exception:
                 traffic = None
         line = {
@@ -273,7 +318,9 @@ def run_ours(args):
                          "frac": (achieved_tf / peak_tf.value) if (achieved_tf and peak_tf.value) else None, "traffic": traffic,
                          "kernel": "ensemble_kernel<double, coupled, write>", "kernel_ms": kernel_ms,
                          "algorithmic": "1710 flop per member-year (SURVEY.md 8d) x %d member-years per launch" % per_launch_my,
-                         "peak_source": "DFMA micro-benchmark in this run (rscm_b200_measure_fma_peak); MEASURED_PEAKS.json has no FP64 entry"},
+                         "peak_source": "DFMA micro-benchmark in this run (rscm_b200_measure_fma_peak); MEASURED_PEAKS.json has no FP64 entry",
+                         "note": "frac > 1 is possible: the kernel executes fewer FP64 operations than the reference's expression count "
+                                 "(DESIGN.md 2.2); the committed ncu capture gives the pipe's own utilisation", "ncu": ncu_pipe},
             "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": (achieved_gbs / hbm_peak) if achieved_gbs else None, "peak_source": hbm_src,
                              "algorithmic": "56 B written per member-year"},

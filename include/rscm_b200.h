@@ -294,6 +294,30 @@ double rscm_b200_kernel_ms(rscm_b200_ensemble *h, int reset);
  * throughput of `device` in TFLOP/s (2 flop per FMA) */
 int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops);
 
+/* ---- ensemble sampler: the stretch move on the device ------------------------
+ * Replaces the per-walker host loops of EnsembleSampler::update_group
+ * (crates/rscm-calibrate/src/sampler/ensemble.rs:489-546) around the
+ * log_posterior_batch call: StretchMove::propose / sample_z (moves.rs:55-59,
+ * 110-125) and acceptance_probability + accept/reject (moves.rs:76-92,
+ * ensemble.rs:520-543).  All pointers are DEVICE pointers on the current device;
+ * positions are SoA: (column c, walker w) at positions[c*ld + w]; the active half
+ * is [active_begin, active_begin + n_active), the complementary half
+ * [comp_begin, comp_begin + n_comp).  Every random draw is a pure function of
+ * (seed, walker index, step, purpose) through Philox4x32-10 (the reference uses a
+ * non-reproducible thread_rng: statistical parity only), so ranks that hold the
+ * same walker state take identical decisions.  `step` must differ between the two
+ * half-updates of an iteration (e.g. 2*iteration + half).
+ *   propose: proposals[c*ld_proposals + i] = x_j + z_i (x_i - x_j), z[i] = z_i, i in [0, n_active)
+ *   accept : walker i takes its proposal (and logpost[w] = logpost_new[i]) with
+ *            probability min(1, z^(n_cols-1) exp(new - old)), 0 when `new` is not finite;
+ *            *n_accepted (may be NULL) is incremented by the number of accepted moves. */
+int rscm_b200_stretch_propose(const double *d_positions, int64_t ld, int n_cols, int64_t active_begin, int64_t n_active,
+                              int64_t comp_begin, int64_t n_comp, double a, uint64_t seed, uint32_t step, double *d_proposals,
+                              int64_t ld_proposals, double *d_z, void *stream);
+int rscm_b200_stretch_accept(double *d_positions, int64_t ld, int n_cols, int64_t active_begin, int64_t n_active,
+                             const double *d_proposals, int64_t ld_proposals, const double *d_z, const double *d_logpost_new,
+                             double *d_logpost, uint64_t seed, uint32_t step, unsigned long long *d_n_accepted, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ from .core import Ensemble, ModelBuilder
 
 __all__ = [
     "Uniform", "Normal", "LogNormal", "Bound", "ParameterSet", "Observation", "VariableTarget", "Target",
-    "GaussianLikelihood", "ModelRunner", "WalkerInit", "Chain", "EnsembleSampler", "ProgressInfo",
+    "GaussianLikelihood", "ModelRunner", "WalkerInit", "Chain", "EnsembleSampler", "DeviceEnsembleSampler", "ProgressInfo",
 ]
 
 _LN_2PI = math.log(2.0 * math.pi)
@@ -439,4 +439,104 @@ class EnsembleSampler:
             if progress is not None:
                 progress(ProgressInfo(it, n_iterations, n_acc / max(1, n_prop), float(np.mean(logp))))
         self.acceptance_rate = n_acc / max(1, n_prop)
+        return chain
+
+
+class DeviceEnsembleSampler(EnsembleSampler):
+    """The same Goodman & Weare loop with nothing but the chain leaving the GPU.
+
+    Walker positions ``[n_params][n_walkers]``, proposals, stretch factors and log-posteriors stay in HBM; one iteration is
+    two (``stretch_propose`` -> fused log-posterior kernel -> ``stretch_accept``) triples on one stream
+    (include/rscm_b200.h; sampler/ensemble.rs:489-546, sampler/moves.rs:55-125).  Random draws are Philox4x32-10
+    functions of (seed, walker, step, purpose), so a run is reproducible from ``seed`` and, under ``torch.distributed``,
+    every rank keeps an identical replica of the walker state: each rank evaluates its member block of the active half and
+    the log-posteriors are all-gathered (rscm_b200/dist.py) — no other exchange.
+    """
+
+    MAX_DEVICE_CHAIN_BYTES = 4 << 30
+
+    def _stream(self):
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+
+    def _evaluate(self, d_params, d_out, n, dist_group):
+        """log-posterior of the n parameter sets in d_params [n_params][n] into d_out [n]."""
+        import torch
+        ens, scen = self.runner.ensemble, self._d_scen
+        S = 0 if scen is None else 1
+        if dist_group is None:
+            ens.log_posterior_device(d_params, scen, d_out, layout=0, M=n, S=S, stream=self._stream())
+            return
+        import torch.distributed as dist
+        from .dist import allgather_members, member_shard
+        g = None if dist_group is True else dist_group
+        lo, hi = member_shard(n, dist.get_rank(g), dist.get_world_size(g))
+        local = torch.empty(hi - lo, dtype=torch.float64, device=d_params.device)
+        if hi > lo:
+            ens.log_posterior_device(d_params[:, lo:hi].contiguous(), scen, local, layout=0, M=hi - lo, S=S, stream=self._stream())
+        d_out.copy_(allgather_members(local, n, g))
+
+    def run(self, n_iterations: int, init: WalkerInit, thin: int = 1, n_walkers: int | None = None, progress=None, *,
+            seed: int | None = None, distributed: bool | object = False) -> Chain:
+        import torch
+
+        W = n_walkers or self._default_n_walkers
+        if W < 2:
+            raise ValueError("Must have at least 2 walkers")
+        if W % 2:
+            raise ValueError("Number of walkers must be even")
+        scen = self.runner._scenarios
+        if scen is not None and scen.shape[0] != 1:
+            raise ValueError("the sampler evaluates one scenario per walker; the runner holds %d" % scen.shape[0])
+        group = (True if distributed is True else distributed) if distributed else None
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._d_scen = None if scen is None else torch.from_numpy(np.ascontiguousarray(scen)).to(dev)
+        P, half, thin = len(self.params), W // 2, max(1, int(thin))
+        if seed is None:
+            seed = int(self._rng.integers(0, 2 ** 63))
+        pos0 = torch.from_numpy(np.ascontiguousarray(init.initialize(W, self.params, self._rng).T)).to(dev)  # [P][W]
+        if group is not None:
+            import torch.distributed as dist
+            meta = torch.tensor([seed], dtype=torch.int64, device=dev)
+            dist.broadcast(meta, 0, group=None if group is True else group)   # one seed, one initial ensemble on every rank
+            dist.broadcast(pos0, 0, group=None if group is True else group)
+            seed = int(meta.item())
+        d_pos = pos0.contiguous()
+        d_logp = torch.empty(W, dtype=torch.float64, device=dev)
+        self._evaluate(d_pos, d_logp, W, group)
+        d_prop = torch.empty((P, half), dtype=torch.float64, device=dev)
+        d_z = torch.empty(half, dtype=torch.float64, device=dev)
+        d_lpn = torch.empty(half, dtype=torch.float64, device=dev)
+        d_nacc = torch.zeros(1, dtype=torch.int64, device=dev)
+        n_keep = (n_iterations + thin - 1) // thin
+        on_device = n_keep * W * (P + 1) * 8 <= self.MAX_DEVICE_CHAIN_BYTES
+        if on_device:
+            d_samples = torch.empty((n_keep, P, W), dtype=torch.float64, device=dev)
+            d_logps = torch.empty((n_keep, W), dtype=torch.float64, device=dev)
+        chain = Chain(self.params.param_names, thin)
+        lib, ptr = _ffi.lib, (lambda t: t.data_ptr())
+        for it in range(n_iterations):
+            for hidx, (a0, c0) in enumerate(((0, half), (half, 0))):
+                step = 2 * it + hidx
+                _ffi.check(lib.rscm_b200_stretch_propose(ptr(d_pos), W, P, a0, half, c0, half, self.a, seed, step, ptr(d_prop), half,
+                                                         ptr(d_z), self._stream()))
+                self._evaluate(d_prop, d_lpn, half, group)
+                _ffi.check(lib.rscm_b200_stretch_accept(ptr(d_pos), W, P, a0, half, ptr(d_prop), half, ptr(d_z), ptr(d_lpn), ptr(d_logp),
+                                                        seed, step, ptr(d_nacc), self._stream()))
+            if it % thin == 0:
+                if on_device:
+                    d_samples[it // thin].copy_(d_pos)
+                    d_logps[it // thin].copy_(d_logp)
+                else:
+                    chain._samples.append(d_pos.T.cpu().numpy())
+                    chain._log_probs.append(d_logp.cpu().numpy())
+            if progress is not None:  # a host read-back per iteration: only when asked for
+                progress(ProgressInfo(it, n_iterations, int(d_nacc.item()) / ((it + 1) * W), float(d_logp.mean().item())))
+        if on_device and n_keep:
+            chain._samples = list(d_samples.permute(0, 2, 1).contiguous().cpu().numpy())
+            chain._log_probs = list(d_logps.cpu().numpy())
+        chain._total = n_iterations
+        self.acceptance_rate = int(d_nacc.item()) / max(1, n_iterations * W)
+        self.final_positions = d_pos.T.cpu().numpy()
+        self.final_log_probs = d_logp.cpu().numpy()
         return chain

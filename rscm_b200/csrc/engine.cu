@@ -18,6 +18,7 @@
 #include "graph.hpp"
 #include "jit.hpp"
 #include "kernel.cuh"
+#include "sampler.cuh"
 
 using rscm_dev::KArgs;
 
@@ -795,6 +796,39 @@ int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops)
     cudaEventDestroy(e1);
     cudaFree(sink);
     *tflops = best;
+    return RSCM_B200_OK;
+}
+
+// ---- stretch move (sampler/moves.rs, sampler/ensemble.rs:489-546) -------------------------------------------------
+int rscm_b200_stretch_propose(const double *d_positions, int64_t ld, int n_cols, int64_t active_begin, int64_t n_active,
+                              int64_t comp_begin, int64_t n_comp, double a, uint64_t seed, uint32_t step, double *d_proposals,
+                              int64_t ld_proposals, double *d_z, void *stream)
+{
+    rscm_b200_ensemble *h = nullptr;
+    if (!d_positions || !d_proposals || !d_z) return fail(nullptr, RSCM_B200_EINVAL, "null argument");
+    if (n_cols < 1 || n_active < 1 || n_comp < 1 || ld < 1 || ld_proposals < n_active)
+        return fail(nullptr, RSCM_B200_EINVAL, "stretch_propose: empty walker set or bad leading dimension");
+    if (!(a > 1.0)) return fail(nullptr, RSCM_B200_EINVAL, "stretch parameter must be > 1"); // moves.rs:36-40
+    const unsigned blocks = static_cast<unsigned>((n_active + 255) / 256);
+    rscm_dev::stretch_propose_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_positions, ld, n_cols, active_begin, n_active, comp_begin, n_comp, a, seed, step, d_proposals, ld_proposals, d_z);
+    CU(cudaGetLastError());
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_stretch_accept(double *d_positions, int64_t ld, int n_cols, int64_t active_begin, int64_t n_active,
+                             const double *d_proposals, int64_t ld_proposals, const double *d_z, const double *d_logpost_new,
+                             double *d_logpost, uint64_t seed, uint32_t step, unsigned long long *d_n_accepted, void *stream)
+{
+    rscm_b200_ensemble *h = nullptr;
+    if (!d_positions || !d_proposals || !d_z || !d_logpost_new || !d_logpost) return fail(nullptr, RSCM_B200_EINVAL, "null argument");
+    if (n_cols < 1 || n_active < 1 || ld < 1 || ld_proposals < n_active)
+        return fail(nullptr, RSCM_B200_EINVAL, "stretch_accept: empty walker set or bad leading dimension");
+    const unsigned blocks = static_cast<unsigned>((n_active + 255) / 256);
+    rscm_dev::stretch_accept_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_positions, ld, n_cols, active_begin, n_active, d_proposals, ld_proposals, d_z, d_logpost_new, d_logpost, seed, step,
+        d_n_accepted);
+    CU(cudaGetLastError());
     return RSCM_B200_OK;
 }
 

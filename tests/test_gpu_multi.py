@@ -78,3 +78,54 @@ def test_two_gpu_sharding_is_bit_identical_to_one_gpu():
     for r in range(2):
         lo, hi, part = ret[f"ts{r}"]
         assert np.array_equal(part.reshape(351, 2, hi - lo), full[:, :, lo:hi])
+
+
+def _sampler_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from rscm_b200.calibrate import DeviceEnsembleSampler, GaussianLikelihood, WalkerInit
+
+        from tests.test_sampler_device import two_layer_problem
+
+        params, runner, target = two_layer_problem()
+        s = DeviceEnsembleSampler(params, runner, GaussianLikelihood(), target, seed=100 + rank)  # rank 0's seed and walkers win
+        chain = s.run(12, WalkerInit.from_prior(), n_walkers=66, seed=(77 if rank == 0 else 78), distributed=True)
+        ret[f"pos{rank}"] = chain._samples[-1]
+        ret[f"first{rank}"] = chain._samples[0]
+        ret[f"acc{rank}"] = s.acceptance_rate
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sampler_replicas_stay_identical_and_match_one_gpu():
+    """Replicated walker state + sharded log-posterior + all-gather: both ranks hold the same chain, and it
+    is the chain one GPU produces from the same seed and initial ensemble (per-member results do not depend on sharding)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert np.array_equal(ret["pos0"], ret["pos1"]) and ret["acc0"] == ret["acc1"] and 0.05 < ret["acc0"] < 0.95
+    from rscm_b200.calibrate import DeviceEnsembleSampler, GaussianLikelihood, WalkerInit
+
+    from tests.test_sampler_device import two_layer_problem
+
+    params, runner, target = two_layer_problem()
+    s = DeviceEnsembleSampler(params, runner, GaussianLikelihood(), target, seed=100)
+    one = s.run(12, WalkerInit.from_prior(), n_walkers=66, seed=77)
+    assert np.array_equal(one._samples[-1], ret["pos0"]) and np.array_equal(one._samples[0], ret["first0"])
