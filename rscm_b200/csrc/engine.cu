@@ -69,8 +69,7 @@ struct rscm_b200_ensemble {
     int device = 0;
     const AotEntry *prog = nullptr;
     bool use_jit = false; // program compiled at run time (jit.cpp) instead of taken from the AOT registry
-    std::string jit_cubin;
-    std::vector<std::string> jit_names;
+    std::string jit_cubin[3], jit_names[3]; // per kernel variant (write / logpost / both), compiled on first use
     rscm::JitProgram jit;
     std::string err;
     int Tpad = 0;
@@ -292,6 +291,14 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     CU(cudaEventRecord(h->events[ei].first, st));
     if (h->use_jit) {
         const int variant = (write && !logp) ? 0 : ((!write && logp) ? 1 : 2);
+        if (!h->jit.fn[variant]) { // first use of this kernel variant: compile (disk-cached) and load it
+            std::string jerr;
+            if (h->jit_cubin[variant].empty() &&
+                !rscm::jit_compile_cubin(g.program_source, h->dtype, variant, h->jit_cubin[variant], h->jit_names[variant], jerr))
+                return fail(h, RSCM_B200_EUNSUPPORTED, "run-time compilation failed: " + jerr);
+            if (!rscm::jit_load(h->jit_cubin[variant], h->jit_names[variant], variant, h->jit, jerr))
+                return fail(h, RSCM_B200_ECUDA, "loading the run-time compiled program failed: " + jerr);
+        }
         const int rc = rscm::jit_launch(h->jit, variant, grid.x, grid.y, rscm_dev::BLOCK, static_cast<unsigned>(smem_bytes(h, logp)), st, &a);
         if (rc != 0) return fail(h, RSCM_B200_ECUDA, "cuLaunchKernel failed with CUresult " + std::to_string(rc));
     } else {
@@ -352,7 +359,9 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
     if (!h->prog) {
         // not one of the ahead-of-time graphs: compile the emitted program at run time (NVRTC)
         std::string jerr;
-        if (!rscm::jit_compile_cubin(g.program_source, h->dtype, h->jit_cubin, h->jit_names, jerr)) {
+        // the plain `write` variant is compiled now (a program that does not compile is refused at creation, also for
+        // host-only handles); the log-posterior variants follow on first use
+        if (!rscm::jit_compile_cubin(g.program_source, h->dtype, 0, h->jit_cubin[0], h->jit_names[0], jerr)) {
             delete h;
             return fail(nullptr, RSCM_B200_EUNSUPPORTED,
                         "no ahead-of-time device program for this component graph and run-time compilation failed "
@@ -389,7 +398,7 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
     if (h->use_jit) {
         cudaFree(nullptr); // make the primary context current for the driver-API module load
         std::string jerr;
-        if (!rscm::jit_load(h->jit_cubin, h->jit_names, h->jit, jerr)) {
+        if (!rscm::jit_load(h->jit_cubin[0], h->jit_names[0], 0, h->jit, jerr)) {
             delete h;
             return fail(nullptr, RSCM_B200_ECUDA, "loading the run-time compiled program failed: " + jerr);
         }

@@ -118,5 +118,38 @@ def main():
                       "cpu_oracle_member_years_per_s": idx.size * 350 / cpu_s, "cpu_threads": orc.max_threads()}), flush=True)
 
 
+def sampler_loop(W=1 << 20, iters=20):
+    """config 5 as a loop: EnsembleSampler iterations over W walkers (two half-ensemble log-posterior evaluations each),
+    host loop (numpy proposals, host<->device copies every half-update) vs DeviceEnsembleSampler (state resident in HBM)."""
+    from rscm_b200.calibrate import (DeviceEnsembleSampler, EnsembleSampler, GaussianLikelihood, ModelRunner, ParameterSet, Target, Uniform,
+                                     WalkerInit)
+    b, binds, _, scen = syn.config2(M=4)
+    runner = ModelRunner(b, binds, ["Surface Temperature"], scenarios=None)
+    runner._scenarios = runner.ensemble.pack_scenarios(scen)
+    truth = dict(syn.TWO_LAYER_DEFAULTS, lambda0=1.1, efficacy=1.3, a=0.05)
+    t_true = runner.run_batch_arrays(np.array([[truth[k] for k in syn.TWO_LAYER_RANGES]]))["Surface Temperature"][:, 0]
+    target = Target()
+    for name, year, value, sigma in syn.config5_observations(t_true, syn.time_axis().values()):
+        target.add_observation(name, year, value, sigma)
+    ps = ParameterSet()
+    for k, (lo, hi) in syn.TWO_LAYER_RANGES.items():
+        ps.add(k, Uniform(lo, hi))
+    res = {}
+    for name, cls, n in (("device", DeviceEnsembleSampler, iters), ("host", EnsembleSampler, max(2, iters // 5))):
+        s = cls(ps, runner, GaussianLikelihood(), target, seed=1)
+        s.run(2, WalkerInit.from_prior(), n_walkers=W, thin=1000)   # warm-up (allocations, first launches)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s.run(n, WalkerInit.from_prior(), n_walkers=W, thin=1000)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n
+        res[name] = {"s_per_iteration": dt, "member_years_per_s": W * 350 / dt, "acceptance_rate": s.acceptance_rate}
+    print(json.dumps({"config": "5 (loop): ensemble sampler iterations, %d walkers, 6 parameters, 171 observations" % W, **res,
+                      "note": "per iteration: 2 half-updates = W log-posterior evaluations; timing includes the initial W-walker evaluation"}),
+          flush=True)
+
+
 if __name__ == "__main__":
     main()
+    if not sys.argv[1:] or "5" in sys.argv[1:]:
+        sampler_loop()
