@@ -44,6 +44,9 @@ class Uniform:
     def sample(self, rng=None) -> float:
         return float((rng or np.random.default_rng()).uniform(self._low, self._high))
 
+    def sample_n(self, n: int, rng=None) -> np.ndarray:
+        return (rng or np.random.default_rng()).uniform(self._low, self._high, size=n)
+
     def ln_pdf(self, x: float) -> float:  # :157-163
         return -math.inf if (x < self._low or x > self._high) else -math.log(self._high - self._low)
 
@@ -65,6 +68,9 @@ class Normal:
 
     def sample(self, rng=None) -> float:
         return float((rng or np.random.default_rng()).normal(self._mean, self._std))
+
+    def sample_n(self, n: int, rng=None) -> np.ndarray:
+        return (rng or np.random.default_rng()).normal(self._mean, self._std, size=n)
 
     def ln_pdf(self, x: float) -> float:  # :256-259
         z = (x - self._mean) / self._std
@@ -88,6 +94,9 @@ class LogNormal:
 
     def sample(self, rng=None) -> float:
         return float((rng or np.random.default_rng()).lognormal(self._mu, self._sigma))
+
+    def sample_n(self, n: int, rng=None) -> np.ndarray:
+        return (rng or np.random.default_rng()).lognormal(self._mu, self._sigma, size=n)
 
     def ln_pdf(self, x: float) -> float:  # :353-360
         if x <= 0.0:
@@ -116,6 +125,19 @@ class Bound:
             x = self._dist.sample(rng)
             if self._low <= x <= self._high:
                 return x
+        raise RuntimeError("Bound.sample: rejection sampling failed")
+
+    def sample_n(self, n: int, rng=None) -> np.ndarray:
+        """Vectorised rejection sampling (same acceptance rule as `sample`)."""
+        out = np.empty(n)
+        todo = np.arange(n)
+        for _ in range(10000):
+            x = self._dist.sample_n(todo.size, rng)
+            ok = (x >= self._low) & (x <= self._high)
+            out[todo[ok]] = x[ok]
+            todo = todo[~ok]
+            if todo.size == 0:
+                return out
         raise RuntimeError("Bound.sample: rejection sampling failed")
 
     def ln_pdf(self, x: float) -> float:
@@ -149,8 +171,9 @@ class ParameterSet:
         return list(self._params)
 
     def sample_random(self, n: int, rng=None) -> np.ndarray:
+        """[n, n_params]: n independent draws of every parameter (parameter_set.rs sample_random), drawn column by column."""
         rng = rng or np.random.default_rng()
-        return np.array([[d.sample(rng) for d in self._params.values()] for _ in range(n)])
+        return np.column_stack([d.sample_n(n, rng) for d in self._params.values()]) if len(self) else np.empty((n, 0))
 
     def sample_lhs(self, n: int, rng=None) -> np.ndarray:
         rng = rng or np.random.default_rng()
