@@ -318,6 +318,18 @@ int rscm_b200_stretch_accept(double *d_positions, int64_t ld, int n_cols, int64_
                              const double *d_proposals, int64_t ld_proposals, const double *d_z, const double *d_logpost_new,
                              double *d_logpost, uint64_t seed, uint32_t step, unsigned long long *d_n_accepted, void *stream);
 
+/* ---- ensemble summaries on the device -----------------------------------------
+ * Quantiles across members of an output block d_out[rows][S*M] (the layout of
+ * rscm_b200_run_device), per row and scenario: d_result[nq][rows][S].  This is the
+ * across-member percentile band users of the reference compute with pandas /
+ * numpy over looped Model::run results (docs/notebooks/scenario_pipeline.py:
+ * 339-400; python/rscm/calibrate/pandas_helpers.py); on the device it replaces the
+ * copy of the whole block to the host.  NaNs are ignored and interpolation is
+ * numpy's "linear" method: results equal numpy.nanquantile bit for bit.  `q` is a
+ * HOST array of 1..5 values in [0, 1]; d_out / d_result are device pointers. */
+int rscm_b200_member_quantiles(const double *d_out, int64_t rows, int64_t S, int64_t M, const double *q, int nq, double *d_result,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,6 +145,7 @@ SYMBOLS = {
     "rscm_b200_launch_count": (C.c_int64, [_H]),
     "rscm_b200_kernel_ms": (C.c_double, [_H, C.c_int]),
     "rscm_b200_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "rscm_b200_member_quantiles": (C.c_int, [_PD, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.c_int, _PD, C.c_void_p]),
     "rscm_b200_stretch_propose": (C.c_int, [_PD, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_uint64,
                                             C.c_uint32, _PD, C.c_int64, _PD, C.c_void_p]),
     "rscm_b200_stretch_accept": (C.c_int, [_PD, C.c_int64, C.c_int, C.c_int64, C.c_int64, _PD, C.c_int64, _PD, _PD, _PD, C.c_uint64,

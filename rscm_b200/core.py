@@ -719,6 +719,40 @@ class Ensemble:
             self._h,
         )
 
+    # -- summaries across members ------------------------------------
+    def member_quantiles_device(self, out, q: Sequence[float], result, *, M: int, S: int = 1, stream: int = 0) -> None:
+        """Quantiles across members of a device output block ``out`` [rows][S*M] into ``result`` [len(q)][rows][S]
+        (CUDA tensors or raw pointers; asynchronous; at most 5 quantiles per call)."""
+        qs = (C.c_double * len(q))(*[float(x) for x in q])
+        _ffi.check(_ffi.lib.rscm_b200_member_quantiles(self._ptr(out), self.output_rows, max(S, 1), M, qs, len(q), self._ptr(result), stream))
+
+    def run_quantiles(self, params: np.ndarray, scenarios: np.ndarray | None, q: Sequence[float], *, layout: int = 1) -> dict[str, np.ndarray]:
+        """Run the ensemble and return, instead of every member's series, their across-member quantiles per scenario:
+        ``{variable: [len(q), T_sel, R, S]}`` (R squeezed for scalars).  The member outputs never leave the GPU — what a
+        notebook of the reference gets from ``np.nanquantile`` over looped ``Model.run()`` results, without the loop or the copy.
+        Needs the whole output block in device memory at once."""
+        import torch
+
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        M = p.shape[0] if layout == 1 else p.shape[1]
+        if scenarios is None and self.exogenous_names:
+            scenarios = self.default_scenarios()
+        S = 1 if scenarios is None else scenarios.shape[0]
+        rows = self.output_rows
+        d_p = torch.from_numpy(np.ascontiguousarray(p.T) if layout == 1 else p).cuda()
+        d_s = None if scenarios is None else torch.from_numpy(np.ascontiguousarray(scenarios, dtype=np.float64)).cuda()
+        d_o = torch.empty((rows, S * M), dtype=torch.float64, device="cuda")
+        self.run_device(d_p, d_s, d_o, layout=0, M=M, S=0 if d_s is None else S)
+        res = torch.empty((len(q), rows, S), dtype=torch.float64, device="cuda")
+        for k0 in range(0, len(q), 5):
+            self.member_quantiles_device(d_o, q[k0:k0 + 5], res[k0:k0 + 5], M=M, S=S)
+        host = res.cpu().numpy()
+        out = {}
+        for name, (row, nt, r) in self.output_layout().items():
+            blk = host[:, row:row + nt * r, :].reshape(len(q), nt, r, S)
+            out[name] = blk[:, :, 0, :] if r == 1 else blk
+        return out
+
     def run(self, params: np.ndarray | None, scenarios: np.ndarray | None = None, *, layout: int = 1, out: np.ndarray | None = None,
             status: np.ndarray | None = None) -> np.ndarray:
         """Host entry point: ``params`` [M, n_cols] (layout 1, one row per member like the

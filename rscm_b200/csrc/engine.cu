@@ -19,6 +19,7 @@
 #include "jit.hpp"
 #include "kernel.cuh"
 #include "sampler.cuh"
+#include "summary.cuh"
 
 using rscm_dev::KArgs;
 
@@ -837,6 +838,34 @@ int rscm_b200_stretch_accept(double *d_positions, int64_t ld, int n_cols, int64_
     rscm_dev::stretch_accept_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         d_positions, ld, n_cols, active_begin, n_active, d_proposals, ld_proposals, d_z, d_logpost_new, d_logpost, seed, step,
         d_n_accepted);
+    CU(cudaGetLastError());
+    return RSCM_B200_OK;
+}
+
+// ---- across-member quantiles of an output block (summary.cuh) -------------------------------------------------------
+int rscm_b200_member_quantiles(const double *d_out, int64_t rows, int64_t S, int64_t M, const double *q, int nq, double *d_result,
+                               void *stream)
+{
+    rscm_b200_ensemble *h = nullptr;
+    if (!d_out || !q || !d_result) return fail(nullptr, RSCM_B200_EINVAL, "null argument");
+    if (rows < 1 || S < 1 || M < 1) return fail(nullptr, RSCM_B200_EINVAL, "member_quantiles: empty output block");
+    if (nq < 1 || nq > rscm_dev::Q_MAXQ) return fail(nullptr, RSCM_B200_EINVAL, "member_quantiles: 1 to 5 quantiles per call");
+    if (rows * S > 2147483647LL) return fail(nullptr, RSCM_B200_EINVAL, "member_quantiles: too many (row, scenario) segments");
+    rscm_dev::QArgs a{};
+    a.data = d_out;
+    a.M = M;
+    a.runs = S * M;
+    a.S = static_cast<int>(S);
+    a.nq = nq;
+    for (int k = 0; k < nq; ++k) {
+        if (!(q[k] >= 0.0 && q[k] <= 1.0)) return fail(nullptr, RSCM_B200_EINVAL, "quantiles must be in the range [0, 1]");
+        a.q[k] = q[k];
+    }
+    a.result = d_result;
+    a.rows = rows;
+    const size_t smem = sizeof(rscm_dev::QShared);
+    CU(cudaFuncSetAttribute(rscm_dev::member_quantiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    rscm_dev::member_quantiles_kernel<<<static_cast<unsigned>(rows * S), rscm_dev::Q_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
     CU(cudaGetLastError());
     return RSCM_B200_OK;
 }

@@ -149,7 +149,38 @@ def sampler_loop(W=1 << 20, iters=20):
           flush=True)
 
 
+def summaries(M=262_144):
+    """F3: across-member quantiles of the headline workload's output block, where it lives."""
+    b, binds, params, scen = syn.config3(M=M, S=8)
+    ens = b.build_ensemble().bind_parameters(binds)
+    sc = torch.from_numpy(ens.pack_scenarios(scen)).cuda()
+    d_p = torch.from_numpy(np.ascontiguousarray(params.T)).cuda()
+    q = [0.05, 0.17, 0.5, 0.83, 0.95]
+    for label, outs in (("Surface Temperature", ["Surface Temperature"]), ("all 7 series", syn.COUPLED_OUTPUTS)):
+        ens.select_outputs(outs)
+        d_o = torch.empty((ens.output_rows, 8 * M), dtype=torch.float64, device="cuda")
+        ens.run_device(d_p, sc, d_o, layout=0)
+        res = torch.empty((5, ens.output_rows, 8), dtype=torch.float64, device="cuda")
+        ms = time_launches(lambda: ens.member_quantiles_device(d_o, q, res, M=M, S=8), reps=3, warm=1)
+        nbytes = ens.output_rows * 8 * M * 8
+        # parity of a strided row subsample against numpy
+        rows = np.arange(0, ens.output_rows, max(1, ens.output_rows // 12))
+        host = d_o[torch.from_numpy(rows).cuda()].cpu().numpy().reshape(rows.size, 8, M)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = np.nanquantile(host, q, axis=2)
+        ok = bool(np.array_equal(res.cpu().numpy()[:, rows, :], want, equal_nan=True))
+        print(json.dumps({"config": "3 (summary): 5 quantiles across %d members x 8 scenarios, %s" % (M, label), "rows": ens.output_rows,
+                          "block_GB": nbytes / 1e9, "ms": ms, "block_GB_per_s": nbytes / 1e9 / (ms * 1e-3),
+                          "d2h_bytes_instead_of_block": int(res.numel() * 8), "bit_identical_to_numpy_on_subsample": ok}), flush=True)
+        del d_o, res
+
+
 if __name__ == "__main__":
+    if "summary" in sys.argv[1:]:
+        summaries()
+        sys.exit(0)
     main()
     if not sys.argv[1:] or "5" in sys.argv[1:]:
         sampler_loop()
