@@ -473,6 +473,7 @@ void rscm_b200_ensemble_destroy(rscm_b200_ensemble *h)
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     }
     for (auto &e : h->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (h->use_jit) rscm::jit_unload(h->jit);
     cudaGetLastError();
     delete h;
 }

@@ -16,6 +16,7 @@ std::string jit_source(const std::string &program_body);
 bool jit_compile_cubin(const std::string &program_body, int dtype, int variant, std::string &cubin, std::string &lowered,
                        std::string &err);
 bool jit_load(const std::string &cubin, const std::string &lowered, int variant, JitProgram &out, std::string &err);
+void jit_unload(JitProgram &p);
 // returns the CUresult of cuLaunchKernel (0 = success)
 int jit_launch(const JitProgram &p, int variant, unsigned gx, unsigned gy, unsigned block, unsigned smem, void *stream, void *kargs);
 
