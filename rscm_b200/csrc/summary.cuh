@@ -8,11 +8,13 @@
 // One CTA per (row, scenario) segment of M contiguous values.  Exact order statistics by most-significant-digit radix
 // selection on order-preserving 64-bit keys, all requested ranks at once:
 //   * every quantile needs two order statistics (numpy "linear" interpolation); their ranks form <= QT_MAX sorted targets;
+//   * a first pass finds the count, minimum and maximum key: members of one ensemble share sign and most exponent bits,
+//     so the digits start after the common prefix of min and max (registers and shuffles only, no atomics);
 //   * targets that share a key prefix form a group with one 2048-bin shared-memory histogram of the next 11 key bits;
-//     a pass streams the segment once, finds each element's group by binary search over the (sorted) group prefixes and
-//     adds to its histogram with warp-aggregated atomics (the sign/exponent digit is nearly constant across members);
+//     a pass streams the segment once, finds each element's group by comparing against the (sorted, <= 10) group
+//     prefixes held in registers and adds to its histogram with warp-aggregated atomics;
 //   * a group whose bin holds <= Q_CAP elements switches to collecting them into shared memory, where the wanted ranks
-//     are picked by counting — for smooth data that is the third pass (11 + 11 bits narrow 262 144 members to ~100);
+//     are picked by counting — for smooth data that is the third pass (11 bits narrow 262 144 members to a few hundred);
 //   * NaNs are excluded (numpy.nanquantile semantics); an all-NaN segment gives NaN.
 // Interpolation follows numpy's _lerp (lib/_function_base_impl.py) without FMA contraction, so results are bit-identical
 // to numpy.nanquantile(..., method="linear").
@@ -25,7 +27,7 @@ constexpr int QT_MAX = 2 * Q_MAXQ;     // target order statistics per segment
 constexpr int Q_BITS = 11, Q_BINS = 1 << Q_BITS;
 constexpr int Q_CAP = 512;             // collected candidates per group
 constexpr int Q_THREADS = 1024;
-constexpr int Q_UNROLL = 4;
+constexpr int Q_UNROLL = 8;
 
 struct QArgs {
     const double *data; // [rows][S*M]
@@ -76,38 +78,54 @@ __global__ void __launch_bounds__(Q_THREADS, 1) member_quantiles_kernel(const QA
     const double *seg = a.data + row * a.runs + static_cast<long long>(s) * a.M;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NWARPS = Q_THREADS / 32;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    // ---- pass 0: histogram of the top digit over all non-NaN values --------------------------------------------
-    for (int i = tid; i < Q_BINS; i += Q_THREADS) sh.hist[0][i] = 0u;
-    __syncthreads();
-    for (long long base = tid; base < a.M; base += Q_UNROLL * Q_THREADS) {
-        double xs[Q_UNROLL]; // independent loads first: memory-level parallelism for the streaming pass
+    // ---- pass 0: count, smallest and largest key of the non-NaN values (registers + shuffles only) ---------------
+    // Members of one ensemble share sign and most exponent bits: the digits start after the common prefix of min and max.
+    {
+        unsigned long long kmin = ~0ull, kmax = 0ull;
+        long long cnt = 0;
+        for (long long base = tid; base < a.M; base += Q_UNROLL * Q_THREADS) {
+            double xs[Q_UNROLL]; // independent loads first: memory-level parallelism for the streaming pass
 #pragma unroll
-        for (int u = 0; u < Q_UNROLL; ++u) {
-            const long long i = base + static_cast<long long>(u) * Q_THREADS;
-            xs[u] = i < a.M ? seg[i] : __longlong_as_double(0x7ff8000000000000LL);
-        }
+            for (int u = 0; u < Q_UNROLL; ++u) {
+                const long long i = base + static_cast<long long>(u) * Q_THREADS;
+                xs[u] = i < a.M ? seg[i] : qnan;
+            }
 #pragma unroll
-        for (int u = 0; u < Q_UNROLL; ++u) {
-            const double x = xs[u];
-            if (x == x) {
-                const unsigned d = static_cast<unsigned>(q_key(x) >> (64 - Q_BITS));
-                const unsigned peers = __match_any_sync(__activemask(), d);
-                if (lane == __ffs(peers) - 1) atomicAdd(&sh.hist[0][d], static_cast<unsigned>(__popc(peers)));
+            for (int u = 0; u < Q_UNROLL; ++u) {
+                if (xs[u] == xs[u]) {
+                    const unsigned long long k = q_key(xs[u]);
+                    kmin = k < kmin ? k : kmin;
+                    kmax = k > kmax ? k : kmax;
+                    ++cnt;
+                }
             }
         }
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long omin = __shfl_down_sync(0xffffffffu, kmin, off), omax = __shfl_down_sync(0xffffffffu, kmax, off);
+            kmin = omin < kmin ? omin : kmin;
+            kmax = omax > kmax ? omax : kmax;
+            cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+        }
+        // per-warp partials through the (not yet used) candidate buffers
+        if (lane == 0) { sh.buf[0][warp] = kmin; sh.buf[1][warp] = kmax; sh.buf[2][warp] = static_cast<unsigned long long>(cnt); }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NWARPS; ++w) {
+                kmin = sh.buf[0][w] < kmin ? sh.buf[0][w] : kmin;
+                kmax = sh.buf[1][w] > kmax ? sh.buf[1][w] : kmax;
+                cnt += static_cast<long long>(sh.buf[2][w]);
+            }
+            sh.n = cnt;
+            sh.tprefix[0] = kmin;
+            sh.tprefix[1] = kmax;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (warp == 0) { // n = number of non-NaN values
-        unsigned long long c = 0;
-        for (int i = lane; i < Q_BINS; i += 32) c += sh.hist[0][i];
-        for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
-        if (lane == 0) sh.n = static_cast<long long>(c);
-    }
-    __syncthreads();
     const long long n = sh.n;
     if (n == 0) {
-        if (tid < a.nq) a.result[(static_cast<long long>(tid) * a.rows + row) * a.S + s] = __longlong_as_double(0x7ff8000000000000LL);
+        if (tid < a.nq) a.result[(static_cast<long long>(tid) * a.rows + row) * a.S + s] = qnan;
         return;
     }
     if (tid == 0) {
@@ -138,24 +156,104 @@ __global__ void __launch_bounds__(Q_THREADS, 1) member_quantiles_kernel(const QA
                 if (ranks[t] == hi_rank[k]) sh.qhi[k] = t;
             }
         sh.ntargets = nt;
-        for (int t = 0; t < nt; ++t) { sh.trank[t] = ranks[t]; sh.tdone[t] = 0; }
-        // one group (empty prefix) owning every target; its histogram of the first digit is hist[0]
+        const unsigned long long kmin = sh.tprefix[0], kmax = sh.tprefix[1];
+        const int common = kmin == kmax ? 64 : __clzll(static_cast<long long>(kmin ^ kmax));
+        for (int t = 0; t < nt; ++t) {
+            sh.trank[t] = ranks[t];
+            sh.tdone[t] = common == 64; // every value is the same
+            sh.tkey[t] = kmin;
+        }
+        // one group owning every target: the common prefix of all keys
         sh.ngroups = 1;
         sh.gbeg[0] = 0;
         sh.gend[0] = nt;
-        sh.gprefix[0] = 0ull;
-        sh.gcount[0] = 0xffffffffu; // histogram mode
-        sh.bits = 0;
+        sh.gprefix[0] = common == 0 ? 0ull : (kmin >> (64 - common));
+        sh.gcount[0] = n > 0xffffffffLL ? 0xffffffffu : static_cast<unsigned>(n);
+        sh.gfill[0] = 0u;
+        sh.bits = common;
+        sh.pending = common == 64 ? 0 : nt;
+        sh.any_hist = n > Q_CAP;
     }
     __syncthreads();
 
-    for (;;) {
-        // ---- resolve: every target of a histogram group moves into the bin that holds its rank --------------------
+    while (sh.pending != 0) {
+        // ---- one pass over the segment: histogram the next digit of large groups, collect the small ones -----------
         const int ng = sh.ngroups, bits = sh.bits;
         const int width = (64 - bits < Q_BITS) ? 64 - bits : Q_BITS;
+        for (int g = 0; g < ng; ++g)
+            if (sh.gcount[g] > Q_CAP)
+                for (int i = tid; i < Q_BINS; i += Q_THREADS) sh.hist[g][i] = 0u;
+        // group prefixes in registers (ascending; unused slots compare greater than every prefix) and which groups
+        // histogram (bit g) instead of collecting
+        unsigned long long gp[QT_MAX];
+        unsigned histmask = 0u;
+#pragma unroll
+        for (int g = 0; g < QT_MAX; ++g) {
+            gp[g] = g < ng ? sh.gprefix[g] : ~0ull;
+            if (g < ng && sh.gcount[g] > Q_CAP) histmask |= 1u << g;
+        }
+        const bool no_prefix = bits == 0, single = ng == 1;
+        const int dshift = 64 - bits - width;
+        const unsigned long long dmask = (1ull << width) - 1ull;
+        __syncthreads();
+        for (long long base = tid; base < a.M; base += Q_UNROLL * Q_THREADS) {
+            double xs[Q_UNROLL];
+#pragma unroll
+            for (int u = 0; u < Q_UNROLL; ++u) {
+                const long long i = base + static_cast<long long>(u) * Q_THREADS;
+                xs[u] = i < a.M ? seg[i] : qnan;
+            }
+#pragma unroll
+            for (int u = 0; u < Q_UNROLL; ++u) {
+                const double x = xs[u];
+                if (x != x) continue;
+                const unsigned long long key = q_key(x), pre = no_prefix ? 0ull : key >> (64 - bits);
+                int g = 0;
+                bool hit;
+                if (single) { // the first histogram pass: one group, (nearly) every element belongs to it
+                    hit = pre == gp[0];
+                } else {
+                    hit = false;
+#pragma unroll
+                    for (int j = 0; j < QT_MAX; ++j) { // prefixes are sorted and distinct: #smaller = index of the equal one
+                        g += gp[j] < pre;
+                        hit |= gp[j] == pre;
+                    }
+                }
+                if (!hit) continue;
+                if ((histmask >> g) & 1u) {
+                    // plain shared-memory atomics: after the common prefix the digits are spread over the bins
+                    atomicAdd(&sh.hist[g][static_cast<unsigned>((key >> dshift) & dmask)], 1u);
+                } else {
+                    const unsigned p = atomicAdd(&sh.gfill[g], 1u);
+                    if (p < Q_CAP) sh.buf[g][p] = key;
+                }
+            }
+        }
+        __syncthreads();
+        // collected groups: each target's order statistic by counting (one warp per target; ties give the same key)
         for (int g = 0; g < ng; ++g) {
-            if (sh.gcount[g] <= Q_CAP) continue; // collected group: its targets are done
-            for (int t = sh.gbeg[g] + warp; t < sh.gend[g]; t += NWARPS) { // one warp per target
+            if (sh.gcount[g] > Q_CAP) continue;
+            const int c = static_cast<int>(sh.gcount[g]);
+            for (int t = sh.gbeg[g] + warp; t < sh.gend[g]; t += NWARPS) {
+                const long long r = sh.trank[t];
+                for (int e = lane; e < c; e += 32) {
+                    const unsigned long long ke = sh.buf[g][e];
+                    int less = 0, leq = 0;
+                    for (int j = 0; j < c; ++j) {
+                        const unsigned long long kj = sh.buf[g][j];
+                        less += kj < ke;
+                        leq += kj <= ke;
+                    }
+                    if (less <= r && r < leq) sh.tkey[t] = ke;
+                }
+                if (lane == 0) sh.tdone[t] = 1;
+            }
+        }
+        // histogram groups: every target moves into the bin that holds its rank (one warp per target)
+        for (int g = 0; g < ng; ++g) {
+            if (sh.gcount[g] <= Q_CAP) continue;
+            for (int t = sh.gbeg[g] + warp; t < sh.gend[g]; t += NWARPS) {
                 const unsigned long long r = static_cast<unsigned long long>(sh.trank[t]);
                 const int nb = 1 << width, per = (nb + 31) / 32;
                 unsigned long long mine = 0;
@@ -184,7 +282,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) member_quantiles_kernel(const QA
         if (tid == 0) {
             // regroup: maximal runs of unfinished targets with equal prefixes (targets are sorted by rank, hence by key)
             const int nbits = bits + width;
-            int g2 = 0, pending = 0, any_hist = 0;
+            int g2 = 0, pending = 0;
             for (int t = 0; t < sh.ntargets; ++t) {
                 if (sh.tdone[t]) continue;
                 if (nbits == 64) { // the prefix is the whole key
@@ -201,78 +299,14 @@ __global__ void __launch_bounds__(Q_THREADS, 1) member_quantiles_kernel(const QA
                     sh.gfill[g2] = 0u;
                     sh.gbeg[g2] = t;
                     sh.gend[g2] = t + 1;
-                    any_hist |= sh.tcount[t] > Q_CAP;
                     ++g2;
                 }
             }
             sh.ngroups = g2;
             sh.bits = nbits;
             sh.pending = pending;
-            sh.any_hist = any_hist;
         }
         __syncthreads();
-        if (sh.pending == 0) break;
-
-        // ---- one pass over the segment: histogram the next digit of large groups, collect the small ones -----------
-        const int ng2 = sh.ngroups, b2 = sh.bits;
-        const int w2 = (64 - b2 < Q_BITS) ? 64 - b2 : Q_BITS;
-        for (int g = 0; g < ng2; ++g)
-            if (sh.gcount[g] > Q_CAP)
-                for (int i = tid; i < Q_BINS; i += Q_THREADS) sh.hist[g][i] = 0u;
-        __syncthreads();
-        for (long long base = tid; base < a.M; base += Q_UNROLL * Q_THREADS) {
-          double xs[Q_UNROLL];
-#pragma unroll
-          for (int u = 0; u < Q_UNROLL; ++u) {
-              const long long i = base + static_cast<long long>(u) * Q_THREADS;
-              xs[u] = i < a.M ? seg[i] : __longlong_as_double(0x7ff8000000000000LL);
-          }
-#pragma unroll
-          for (int u = 0; u < Q_UNROLL; ++u) {
-            const double x = xs[u];
-            if (x != x) continue;
-            const unsigned long long key = q_key(x), pre = key >> (64 - b2);
-            int lo = 0, hi = ng2; // first group with prefix >= pre (group prefixes ascend)
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (sh.gprefix[mid] < pre) lo = mid + 1;
-                else hi = mid;
-            }
-            if (lo < ng2 && sh.gprefix[lo] == pre) {
-                if (sh.gcount[lo] > Q_CAP) {
-                    const unsigned d = static_cast<unsigned>((key >> (64 - b2 - w2)) & ((1ull << w2) - 1ull));
-                    const unsigned slot = (static_cast<unsigned>(lo) << Q_BITS) | d;
-                    const unsigned peers = __match_any_sync(__activemask(), slot);
-                    if (lane == __ffs(peers) - 1) atomicAdd(&sh.hist[lo][d], static_cast<unsigned>(__popc(peers)));
-                } else {
-                    const unsigned p = atomicAdd(&sh.gfill[lo], 1u);
-                    if (p < Q_CAP) sh.buf[lo][p] = key;
-                }
-            }
-          }
-        }
-        __syncthreads();
-        // collected groups: each target's order statistic by counting (one warp per target; ties give the same key)
-        for (int g = 0; g < ng2; ++g) {
-            if (sh.gcount[g] > Q_CAP) continue;
-            const int c = static_cast<int>(sh.gcount[g]);
-            for (int t = sh.gbeg[g] + warp; t < sh.gend[g]; t += NWARPS) {
-                const long long r = sh.trank[t];
-                for (int e = lane; e < c; e += 32) {
-                    const unsigned long long ke = sh.buf[g][e];
-                    int less = 0, leq = 0;
-                    for (int j = 0; j < c; ++j) {
-                        const unsigned long long kj = sh.buf[g][j];
-                        less += kj < ke;
-                        leq += kj <= ke;
-                    }
-                    if (less <= r && r < leq) sh.tkey[t] = ke;
-                }
-                if (lane == 0) sh.tdone[t] = 1;
-            }
-        }
-        __syncthreads();
-        if (!sh.any_hist) break; // every remaining group was small enough to collect
     }
 
     if (tid < a.nq) {

@@ -41,7 +41,7 @@ def test_philox_known_answers():
            ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
            ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0], [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1])]
     for c, k, want in kat:
-        assert [int(x) for x in philox4x32_10([[v] for v in c], k)] == want
+        assert [int(x[0]) for x in philox4x32_10([[v] for v in c], k)] == want
 
 
 def test_stretch_factor_distribution_of_the_stream():
