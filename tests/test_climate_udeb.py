@@ -156,3 +156,20 @@ def test_config4_magicc_boxes_parity_and_fp32(tmp_path, monkeypatch):
     print("config4 fp32 relative errors:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert errs["Effective Radiative Forcing"] <= 1e-4
     assert errs["Surface Temperature"] <= 5e-3  # documented divergence: LAMCALC's 1e-3 tolerance iteration + 50-layer Thomas in fp32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_gpu_matches_magicc7_golden(name, tmp_path, monkeypatch):
+    """The same golden comparison as test_oracle_matches_magicc7_golden, but with the fused kernel producing the series
+    (single member through the reference-shaped Model API): the GPU path is pinned to MAGICC7 directly, not only via the oracle."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    years, expected = GOLDEN[name + "/years"], GOLDEN[name + "/temp"]
+    config = json.loads(str(GOLDEN[name + "/config"]))
+    erf = np.where(years >= 1851.0, config.get("core_delq2xco2", 3.71), 0.0)
+    model = udeb_builder(udeb_params(config), years, erf).build()
+    model.run()
+    t4 = np.asarray(model.timeseries().get_fourbox_timeseries_by_name("Surface Temperature").values())
+    actual = t4 @ AREA_W
+    for phase, (err, tol) in phased(actual, expected, **SCENARIOS[name]).items():
+        assert err <= tol, f"{name} {phase}: {err:.4f} > {tol}"

@@ -420,3 +420,29 @@ def test_full_size_coupled_invariants():
     # budget: GTC_PER_PPM * (C - C0) + uptake == cumulative emissions
     closure = 2.13 * (o[2] - 278.0) + o[1] - o[0]
     assert (closure.abs().max() / o[0].abs().max()).item() < 1e-10
+
+
+# ---- irregular time axes and missing data ----------------------------------------------------------------------------
+def test_irregular_time_axis_parity():
+    """Annual, then 5-year, then 10-year steps (tests/test_model.py:9-46 and tests/test_two_layer.py:12-56 run such axes):
+    the RK4 sub-step count follows each step's length (50 and 100 sub-steps), outputs land on the coarse points."""
+    values = np.concatenate([np.arange(1750.0, 1800.0), np.arange(1800.0, 1900.0, 5.0), np.arange(1900.0, 2101.0, 10.0)])
+    axis = TimeAxis.from_values(values)
+    b = syn.coupled_builder(axis=axis)
+    rng = np.random.default_rng(12)
+    params = syn.uniform_params(syn.COUPLED_RANGES, 130, 21)
+    scen = [{"Emissions|CO2|Anthropogenic": np.clip(0.02 * (values - 1750.0) * f + rng.normal(0, 0.1, values.size), 0.0, None)} for f in (1.0, 2.0)]
+    got, _, worst, ens = gpu_vs_oracle(b, syn.COUPLED_BINDINGS, params, scen)
+    assert ens.n_times == values.size and np.isfinite(got["Surface Temperature"]).all() and worst < 1e-10
+
+
+def test_nan_in_the_scenario_propagates_like_the_reference():
+    """A missing (NaN) emission value poisons the carbon cycle from that step on and everything downstream of it, for
+    that scenario only; positions must match the oracle exactly (rel_err asserts it)."""
+    b, binds, params, scen = syn.config3(M=64, S=2)
+    scen[1]["Emissions|CO2|Anthropogenic"] = scen[1]["Emissions|CO2|Anthropogenic"].copy()
+    scen[1]["Emissions|CO2|Anthropogenic"][200] = np.nan
+    got, _, _, _ = gpu_vs_oracle(b, binds, params, scen)
+    conc = got["Atmospheric Concentration|CO2"]
+    assert np.isfinite(conc[:, :64]).all() and np.isfinite(conc[:201, 64:]).all() and np.isnan(conc[201:, 64:]).all()
+    assert np.isnan(got["Surface Temperature"][202:, 64:]).all()
