@@ -124,9 +124,18 @@ __device__ __forceinline__ bool two_layer_solve(const R *, const R *D, const R *
 //   D: 1/tau, step_size/6
 //   in : emissions (get), temperature (get), concentration, cumulative_emissions,
 //        cumulative_uptake (at_start)      out: same three states
-// Hoisted per annual step (inputs are frozen over the step, :144-145):
-//   1/lifetime = exp(-alpha*T) / tau ;  E/GTC_PER_PPM
-// dy[2] = E is constant over the step, so its RK4 increment is one value.
+//
+// The inputs are frozen over a model step (:144-145), so with x = C - C_pi, k = exp(-alpha*T)/tau and
+// e = E/GTC_PER_PPM the right-hand side (:134-158) is LINEAR with constant coefficients:
+//     x' = e - k x,      U' = GTC k x,      E_cum' = E.
+// One classical RK4 step of size h on x' = e - k x is the affine map
+//     x <- P x + c,   q = 1 - z/2 + z^2/6 - z^3/24,  P = 1 - z q,  c = h q e,  z = h k
+// (the degree-4 Taylor polynomial of exp(-z) and its integral), so the reference's n sub-steps are the n-fold
+// composition of that map — formed here by repeated squaring of (P, c) instead of n x 4 right-hand sides.  The uptake
+// needs no stages either: each RK4 step adds h/6 (u0 + 2u1 + 2u2 + u3) GTC with u = k x(stage), and the x update of the
+// same step is x += h e - h/6 (u0 + 2u1 + 2u2 + u3); summed over the n sub-steps:  dU = GTC (n h e - (x_n - x_0)).
+// Same numbers as stepping up to rounding (parity <= 1e-13 against the stepwise oracle), ~30 FP64 operations instead
+// of 170 per model year; exact at equilibrium (x = 0, e = 0 stays 0) and for k = 0.
 // ---------------------------------------------------------------------------
 constexpr int CARBON_CYCLE_NP = 4;
 constexpr int CARBON_CYCLE_ND = 2;
@@ -149,27 +158,22 @@ __device__ __forceinline__ bool carbon_cycle_solve(const R *P, const R *D, const
     R conc = in[2], cum_e = in[3], cum_u = in[4];
     const R inv_life = r_exp<R>(-(alpha * temperature)) * D[0];
     const R e_ppm = emissions * (R(1) / gtc); // reciprocal of the constant: 1 ulp from E/GTC_PER_PPM
-    const R hh = h * R(0.5), h6 = D[1];
-    const R e_inc = (emissions + emissions * R(2) + emissions * R(2) + emissions) * h6;
-    // The concentration is integrated as the anomaly x = C - C_pi (exact subtraction for
-    // C within a factor 2 of C_pi), so uptake u = x/lifetime is one multiply and is
-    // exactly 0 at C = C_pi as in the reference.  dC = e_ppm - u; dU = u*GTC; the
-    // weighted stage sums are formed once on u: sum(dC) = 6 e_ppm - su, sum(dU) = su*GTC.
-    const R e6 = e_ppm * R(6);
-    const R gtc_h6 = gtc * h6;
-    R x = conc - conc_pi;
-#pragma unroll 2
-    for (int s = 0; s < nsub; ++s) {
-        // calculate_dy_dt — carbon_cycle.rs:134-158
-        const R u0 = x * inv_life;
-        const R u1 = (x + (e_ppm - u0) * hh) * inv_life;
-        const R u2 = (x + (e_ppm - u1) * hh) * inv_life;
-        const R u3 = (x + (e_ppm - u2) * h) * inv_life;
-        const R su = u0 + u1 * R(2) + u2 * R(2) + u3;
-        x = x + (e6 - su) * h6;
-        cum_u = cum_u + su * gtc_h6;
-        cum_e = cum_e + e_inc;
+    const R z = h * inv_life;
+    const R q = R(1) + z * (R(-0.5) + z * (R(1.0 / 6.0) + z * R(-1.0 / 24.0)));
+    R pa = R(1) - z * q, pb = h * q * e_ppm; // one RK4 step: x <- pa x + pb
+    R A = R(1), B = R(0);                    // composition of the steps taken so far
+    for (int m = nsub; m > 0; m >>= 1) {     // block-uniform trip count
+        if (m & 1) { B = pa * B + pb; A = pa * A; }
+        pb = pa * pb + pb;
+        pa = pa * pa;
     }
+    // The concentration is integrated as the anomaly x = C - C_pi (exact subtraction for C within a factor 2 of
+    // C_pi), so that uptake is exactly 0 at C = C_pi as in the reference.
+    const R x0 = conc - conc_pi;
+    const R x = A * x0 + B;
+    const R span = R(nsub) * h;
+    cum_u = cum_u + gtc * (span * e_ppm - (x - x0));
+    cum_e = cum_e + span * emissions;
     conc = x + conc_pi;
     out[0] = conc;
     out[1] = cum_e;
