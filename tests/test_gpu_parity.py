@@ -446,3 +446,17 @@ def test_nan_in_the_scenario_propagates_like_the_reference():
     conc = got["Atmospheric Concentration|CO2"]
     assert np.isfinite(conc[:, :64]).all() and np.isfinite(conc[:201, 64:]).all() and np.isnan(conc[201:, 64:]).all()
     assert np.isnan(got["Surface Temperature"][202:, 64:]).all()
+
+
+def test_two_layer_near_runaway_members_keep_parity():
+    """lambda0 - a*T reaches zero near T = lambda0/a: with a close to 0.1 and a weak lambda0 the feedback collapses inside the
+    run and the temperatures blow up (ill-conditioned: rounding is amplified ~1e5 on the way).  These are the members that
+    decide the worst-case parity of BASELINE config 2 — and the ones a cancellation-prone reformulation would break."""
+    b, binds, _, scen = syn.config2(M=4)
+    lam, a = np.meshgrid(np.linspace(0.8, 1.0, 16), np.linspace(0.07, 0.1, 16))
+    params = np.tile(np.array([syn.TWO_LAYER_DEFAULTS[k] for k in syn.TWO_LAYER_RANGES]), (256, 1))
+    params[:, 0], params[:, 1] = lam.ravel(), a.ravel()
+    got, ref, worst, _ = gpu_vs_oracle(b, binds, params, scen)
+    t_end = ref["Surface Temperature"][-1]
+    assert (np.abs(t_end) > 50.0).any() or np.isnan(t_end).any(), "the grid must contain members that run away"
+    assert (np.abs(t_end) < 10.0).any() and worst <= 1e-9
