@@ -1,6 +1,7 @@
 // graph.cpp — host graph compiler (see graph.hpp).
 #include "graph.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -496,6 +497,22 @@ static void emit_program(Graph &g)
     for (int c = 0; c < g.n_cells; ++c)
         if (g.vars[g.cell_var[c]].endogenous) o << "c == " << c << " || ";
     o << "false; }\n";
+    // Cells start every step as NaN ("not written yet", timeseries.rs:334-345).  A cell whose single producer runs
+    // before every node that reads it is overwritten on all paths (a failing component writes NaN explicitly below), so
+    // its blanket NaN store can be dropped; everything else keeps it.
+    std::vector<int> n_writers(g.vars.size(), 0), writer_pos(g.vars.size(), -1), first_reader_pos(g.vars.size(), 1 << 30);
+    for (size_t pos = 0; pos < g.order.size(); ++pos) {
+        const Node &n = g.nodes[g.order[pos]];
+        for (int v : n.in_var) first_reader_pos[v] = std::min(first_reader_pos[v], static_cast<int>(pos));
+        for (int v : n.out_var) { ++n_writers[v]; writer_pos[v] = static_cast<int>(pos); }
+    }
+    o << "    __host__ __device__ static constexpr bool nan_init(int c) { return ";
+    for (int c = 0; c < g.n_cells; ++c) {
+        const int v = g.cell_var[c];
+        const bool safe = n_writers[v] == 1 && writer_pos[v] <= first_reader_pos[v];
+        if (!safe) o << "c == " << c << " || ";
+    }
+    o << "false; }\n";
     o << "    __host__ __device__ static constexpr int regions(int c) { return ";
     for (int c = 0; c < g.n_cells; ++c) {
         const int r = g.vars[g.cell_var[c]].n_regions;
@@ -616,7 +633,12 @@ static void emit_program(Graph &g)
                 }
                 pos += Rc;
             }
-            o << "        } else { fail |= 1u; }\n";
+            o << "        } else {\n            fail |= 1u;\n";
+            for (size_t i = 0; i < n.out_var.size(); ++i) {
+                const Variable &var = g.vars[n.out_var[i]];
+                for (int r = 0; r < var.n_regions; ++r) o << "            nxt[" << (var.cell0 + r) << "] = rscm_dev::r_nan<R>();\n";
+            }
+            o << "        }\n";
         }
         o << "      }\n";
     }

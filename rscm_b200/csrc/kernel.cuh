@@ -255,6 +255,9 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     }
 
     if (total_bytes) mbar_wait(bar, 0);
+    // Padding threads of the last CTA (clamped to run M-1) are only needed for the block-wide reductions of the
+    // log-posterior variants; they must not step (they would race with the real run on its global scratch rows).
+    if (!LOGP && !active) return;
 
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -275,9 +278,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     cx.Tpad = a.Tpad;
     cx.N = 0;
     R S[Prog::NS > 0 ? Prog::NS : 1];
-    // padding threads of the last CTA (clamped to run M-1) must not step: they would race with the real run on its
-    // global scratch rows
-    if (active) Prog::template init_state<R>(P, D, S, cx);
+    if (!LOGP || active) Prog::template init_state<R>(P, D, S, cx);
 
     double ll[MAX_OBS_ROWS] = {0.0, 0.0, 0.0, 0.0};
     bool bad = false;
@@ -310,10 +311,10 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(x_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
-            else nxt[c] = r_nan<R>();
+            else if (Prog::nan_init(c)) nxt[c] = r_nan<R>(); // other cells are overwritten on every path of the step
         }
         cx.N = N;
-        if (active) Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
+        if (!LOGP || active) Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
 
         if (WRITE) {
             if (N + 1 == tnext && tnext < a.t_stop) { // block-uniform
