@@ -381,14 +381,23 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     const int nhist = static_cast<int>(S[US_NHIST]);
     R cum_t = R(0);
     {
-        R rem = P[U_FB_PERIOD], sum = R(0);
+        // Which entries the window covers follows from the time axis alone (shared memory, block-uniform): entries
+        // [first, nhist) count fully, entry first-1 with weight `partial` if the window ends inside it.  The values are
+        // then summed in the reference's order with independent global loads the compiler can batch (a loop that decides
+        // and loads in one go serialises a load latency per year of history: a third of the kernel's time at 350 years).
+        R rem = P[U_FB_PERIOD], partial = R(0);
+        int first = nhist;
         for (int i = nhist - 1; i >= 0; --i) {
             if (rem <= R(0)) break;
             const R dt = R(cx.bounds[i + 1] - cx.bounds[i]);
-            const R h = R(cx.scratch[static_cast<long long>(nr.scr + 2 * UDEB_MAXL + i) * cx.runs]);
-            if (dt <= rem) { sum += h; rem -= dt; }
-            else { sum += h * (rem / dt); rem = R(0); }
+            if (dt <= rem) { first = i; rem -= dt; }
+            else { partial = rem / dt; rem = R(0); }
         }
+        const double *hist = cx.scratch + static_cast<long long>(nr.scr + 2 * UDEB_MAXL) * cx.runs;
+        R sum = R(0);
+#pragma unroll 8
+        for (int i = nhist - 1; i >= first; --i) sum += R(hist[static_cast<long long>(i) * cx.runs]);
+        if (partial > R(0) && first > 0) sum += R(hist[static_cast<long long>(first - 1) * cx.runs]) * partial;
         cum_t = sum;
     }
     const R cumt_2x = P[U_ECS] * P[U_FB_PERIOD];
