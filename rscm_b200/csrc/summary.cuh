@@ -52,6 +52,7 @@ __device__ __forceinline__ double q_unkey(unsigned long long k)
 struct QShared {
     unsigned hist[QT_MAX][Q_BINS];
     unsigned long long buf[QT_MAX][Q_CAP];
+    unsigned lut[Q_BINS]; // bit g set at [low 11 bits of group g's prefix]: most elements miss every group in one lookup
     // groups: targets [gbeg, gend) share the key prefix gprefix (top `bits` bits, right-aligned) carried by gcount elements
     unsigned long long gprefix[QT_MAX];
     unsigned gcount[QT_MAX], gfill[QT_MAX];
@@ -183,18 +184,20 @@ __global__ void __launch_bounds__(Q_THREADS, 1) member_quantiles_kernel(const QA
         for (int g = 0; g < ng; ++g)
             if (sh.gcount[g] > Q_CAP)
                 for (int i = tid; i < Q_BINS; i += Q_THREADS) sh.hist[g][i] = 0u;
-        // group prefixes in registers (ascending; unused slots compare greater than every prefix) and which groups
-        // histogram (bit g) instead of collecting
-        unsigned long long gp[QT_MAX];
+        // which groups histogram (bit g) instead of collecting; group 0's prefix for the single-group pass
         unsigned histmask = 0u;
 #pragma unroll
-        for (int g = 0; g < QT_MAX; ++g) {
-            gp[g] = g < ng ? sh.gprefix[g] : ~0ull;
+        for (int g = 0; g < QT_MAX; ++g)
             if (g < ng && sh.gcount[g] > Q_CAP) histmask |= 1u << g;
-        }
+        const unsigned long long gp0 = sh.gprefix[0];
         const bool no_prefix = bits == 0, single = ng == 1;
         const int dshift = 64 - bits - width;
         const unsigned long long dmask = (1ull << width) - 1ull;
+        if (!single) { // lookup table keyed by the low bits of the prefix (the digit resolved last)
+            for (int i = tid; i < Q_BINS; i += Q_THREADS) sh.lut[i] = 0u;
+            __syncthreads();
+            if (tid < ng) atomicOr(&sh.lut[static_cast<unsigned>(sh.gprefix[tid]) & (Q_BINS - 1)], 1u << tid);
+        }
         __syncthreads();
         for (long long base = tid; base < a.M; base += Q_UNROLL * Q_THREADS) {
             double xs[Q_UNROLL];
@@ -211,13 +214,14 @@ __global__ void __launch_bounds__(Q_THREADS, 1) member_quantiles_kernel(const QA
                 int g = 0;
                 bool hit;
                 if (single) { // the first histogram pass: one group, (nearly) every element belongs to it
-                    hit = pre == gp[0];
+                    hit = pre == gp0;
                 } else {
+                    unsigned cand = sh.lut[static_cast<unsigned>(pre) & (Q_BINS - 1)];
                     hit = false;
-#pragma unroll
-                    for (int j = 0; j < QT_MAX; ++j) { // prefixes are sorted and distinct: #smaller = index of the equal one
-                        g += gp[j] < pre;
-                        hit |= gp[j] == pre;
+                    while (cand) { // rarely more than one candidate: groups whose prefixes share their low 11 bits
+                        const int j = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        if (sh.gprefix[j] == pre) { g = j; hit = true; break; }
                     }
                 }
                 if (!hit) continue;
