@@ -36,6 +36,14 @@
  *     (tests/regression/data/ghg_forcing/*.csv, rtol 1e-5 / atol 1e-6).
  *   - Gaussian likelihood / priors / aggregate: pinned by the reference's
  *     doctest and unit-test known answers.
+ *   - ClimateUDEB: pinned by the MAGICC7 ocean golden runs of the reference's
+ *     regression suite (tests/regression/data/ocean_udeb, phased 1-5 %
+ *     tolerances of tests/regression/test_ocean_udeb.py).
+ *   - The other MAGICC boxes (ozone, aerosols, CH4 / N2O / halocarbon chemistry,
+ *     terrestrial / ocean carbon, CO2 budget, LAMCALC): formulas pinned by the
+ *     known answers of the reference's unit tests (tests/test_magicc_*.py,
+ *     test_ocean_carbon.py, test_halocarbon.py); their multi-decade series:
+ *     PARITY UNPINNED (no reference-generated numbers).
  *   - TwoLayer numeric values: PARITY UNPINNED — the reference's tests for it
  *     are qualitative only (component.rs:300-406).
  */
