@@ -33,7 +33,7 @@
  *     (crates/rscm-components/tests/coupled_models.rs:13-141, rel < 1e-2).
  *   - CO2ERF: pinned by co2_erf.rs:94-113 known answers (1e-10).
  *   - GhgForcing: pinned by the MAGICC7 golden CSVs the reference tests use
- *     (tests/regression/data/ghg_forcing/*.csv, rtol 1e-5 / atol 1e-6).
+ *     (tests/regression/data/ghg_forcing/NN.csv, rtol 1e-5 / atol 1e-6).
  *   - Gaussian likelihood / priors / aggregate: pinned by the reference's
  *     doctest and unit-test known answers.
  *   - ClimateUDEB: pinned by the MAGICC7 ocean golden runs of the reference's
