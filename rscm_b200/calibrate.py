@@ -493,11 +493,15 @@ class DeviceEnsembleSampler(EnsembleSampler):
         import torch.distributed as dist
         from .dist import allgather_members, member_shard
         g = None if dist_group is True else dist_group
-        lo, hi = member_shard(n, dist.get_rank(g), dist.get_world_size(g))
+        world = dist.get_world_size(g)
+        lo, hi = member_shard(n, dist.get_rank(g), world)
         local = torch.empty(hi - lo, dtype=torch.float64, device=d_params.device)
         if hi > lo:
             ens.log_posterior_device(d_params[:, lo:hi].contiguous(), scen, local, layout=0, M=hi - lo, S=S, stream=self._stream())
-        d_out.copy_(allgather_members(local, n, g))
+        if n % world == 0:
+            dist.all_gather_into_tensor(d_out, local, group=g)   # equal contiguous shards: gathered straight into place
+        else:
+            d_out.copy_(allgather_members(local, n, g))
 
     def run(self, n_iterations: int, init: WalkerInit, thin: int = 1, n_walkers: int | None = None, progress=None, *,
             seed: int | None = None, distributed: bool | object = False) -> Chain:

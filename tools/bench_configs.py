@@ -138,15 +138,59 @@ def sampler_loop(W=1 << 20, iters=20):
     for name, cls, n in (("device", DeviceEnsembleSampler, iters), ("host", EnsembleSampler, max(2, iters // 5))):
         s = cls(ps, runner, GaussianLikelihood(), target, seed=1)
         s.run(2, WalkerInit.from_prior(), n_walkers=W, thin=1000)   # warm-up (allocations, first launches)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        s.run(n, WalkerInit.from_prior(), n_walkers=W, thin=1000)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / n
-        res[name] = {"s_per_iteration": dt, "member_years_per_s": W * 350 / dt, "acceptance_rate": s.acceptance_rate}
+        wall = []
+        for k in (n, 3 * n):   # two run lengths: the difference removes walker initialisation and the final read-back
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s.run(k, WalkerInit.from_prior(), n_walkers=W, thin=100000)
+            torch.cuda.synchronize()
+            wall.append(time.perf_counter() - t0)
+        dt = (wall[1] - wall[0]) / (2 * n)
+        res[name] = {"s_per_iteration": dt, "member_years_per_s": W * 350 / dt, "acceptance_rate": s.acceptance_rate,
+                     "setup_and_readback_s": wall[0] - n * dt}
     print(json.dumps({"config": "5 (loop): ensemble sampler iterations, %d walkers, 6 parameters, 171 observations" % W, **res,
-                      "note": "per iteration: 2 half-updates = W log-posterior evaluations; timing includes the initial W-walker evaluation"}),
+                      "note": "per iteration: 2 half-updates = W log-posterior evaluations; steady state from two run lengths"}),
           flush=True)
+
+
+def sampler_loop_distributed(W=1 << 20, iters=30):
+    """config 5 over N GPUs (launch with torchrun): walker state replicated, log-posterior evaluation sharded by member,
+    NCCL all-gather of the per-walker log-posteriors after every half-update (rscm_b200/dist.py)."""
+    import torch.distributed as dist
+    from rscm_b200.calibrate import DeviceEnsembleSampler, GaussianLikelihood, ModelRunner, ParameterSet, Target, Uniform, WalkerInit
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    b, binds, _, scen = syn.config2(M=4)
+    runner = ModelRunner(b, binds, ["Surface Temperature"], scenarios=None, device=local)
+    runner._scenarios = runner.ensemble.pack_scenarios(scen)
+    truth = dict(syn.TWO_LAYER_DEFAULTS, lambda0=1.1, efficacy=1.3, a=0.05)
+    t_true = runner.run_batch_arrays(np.array([[truth[k] for k in syn.TWO_LAYER_RANGES]]))["Surface Temperature"][:, 0]
+    target = Target()
+    for name, year, value, sigma in syn.config5_observations(t_true, syn.time_axis().values()):
+        target.add_observation(name, year, value, sigma)
+    ps = ParameterSet()
+    for k, (lo, hi) in syn.TWO_LAYER_RANGES.items():
+        ps.add(k, Uniform(lo, hi))
+    s = DeviceEnsembleSampler(ps, runner, GaussianLikelihood(), target, seed=1)
+    s.run(3, WalkerInit.from_prior(), n_walkers=W, thin=1000, seed=5, distributed=True)   # warm-up (NCCL, allocations)
+    wall = []
+    for k in (iters, 3 * iters):   # two run lengths: the difference removes walker initialisation and the final read-back
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        s.run(k, WalkerInit.from_prior(), n_walkers=W, thin=100000, seed=6, distributed=True)
+        torch.cuda.synchronize()
+        wall.append(time.perf_counter() - t0)
+    dt = torch.tensor([(wall[1] - wall[0]) / (2 * iters)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"config": "5 (loop, %d GPUs): ensemble sampler iterations, %d walkers, 6 parameters, 171 observations" % (world, W),
+                          "n_gpus": world, "s_per_iteration": float(dt.item()), "member_years_per_s": W * 350 / float(dt.item()),
+                          "acceptance_rate": s.acceptance_rate,
+                          "note": "replicated walker state, sharded log-posterior, all-gather of log-posteriors per half-update; "
+                                  "steady state from two run lengths; max over ranks"}), flush=True)
+    dist.destroy_process_group()
 
 
 def summaries(M=262_144):
@@ -180,6 +224,9 @@ def summaries(M=262_144):
 if __name__ == "__main__":
     if "summary" in sys.argv[1:]:
         summaries()
+        sys.exit(0)
+    if "5dist" in sys.argv[1:]:
+        sampler_loop_distributed()
         sys.exit(0)
     main()
     if not sys.argv[1:] or "5" in sys.argv[1:]:
