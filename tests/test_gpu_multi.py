@@ -80,7 +80,7 @@ def test_two_gpu_sharding_is_bit_identical_to_one_gpu():
         assert np.array_equal(part.reshape(351, 2, hi - lo), full[:, :, lo:hi])
 
 
-def _sampler_worker(rank, world, port, ret):
+def _sampler_worker(rank, world, port, ret, W):
     import torch
     import torch.distributed as dist
 
@@ -94,7 +94,7 @@ def _sampler_worker(rank, world, port, ret):
 
         params, runner, target = two_layer_problem()
         s = DeviceEnsembleSampler(params, runner, GaussianLikelihood(), target, seed=100 + rank)  # rank 0's seed and walkers win
-        chain = s.run(12, WalkerInit.from_prior(), n_walkers=66, seed=(77 if rank == 0 else 78), distributed=True)
+        chain = s.run(12, WalkerInit.from_prior(), n_walkers=W, seed=(77 if rank == 0 else 78), distributed=True)
         ret[f"pos{rank}"] = chain._samples[-1]
         ret[f"first{rank}"] = chain._samples[0]
         ret[f"acc{rank}"] = s.acceptance_rate
@@ -102,7 +102,8 @@ def _sampler_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sampler_replicas_stay_identical_and_match_one_gpu():
+@pytest.mark.parametrize("W", [66, 64])  # ragged shards (padded all-gather) and equal shards (gathered straight into place)
+def test_two_gpu_sampler_replicas_stay_identical_and_match_one_gpu(W):
     """Replicated walker state + sharded log-posterior + all-gather: both ranks hold the same chain, and it
     is the chain one GPU produces from the same seed and initial ensemble (per-member results do not depend on sharding)."""
     import torch
@@ -114,7 +115,7 @@ def test_two_gpu_sampler_replicas_stay_identical_and_match_one_gpu():
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, ret, W)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -127,5 +128,5 @@ def test_two_gpu_sampler_replicas_stay_identical_and_match_one_gpu():
 
     params, runner, target = two_layer_problem()
     s = DeviceEnsembleSampler(params, runner, GaussianLikelihood(), target, seed=100)
-    one = s.run(12, WalkerInit.from_prior(), n_walkers=66, seed=77)
+    one = s.run(12, WalkerInit.from_prior(), n_walkers=W, seed=77)
     assert np.array_equal(one._samples[-1], ret["pos0"]) and np.array_equal(one._samples[0], ret["first0"])
