@@ -460,3 +460,76 @@ def test_two_layer_near_runaway_members_keep_parity():
     t_end = ref["Surface Temperature"][-1]
     assert (np.abs(t_end) > 50.0).any() or np.isnan(t_end).any(), "the grid must contain members that run away"
     assert (np.abs(t_end) < 10.0).any() and worst <= 1e-9
+
+
+# ---- full-size properties of configs 4 and 5 ---------------------------------------------------------------------------
+def test_full_size_config4_determinism_heat_budget_and_subsample_parity(tmp_path, monkeypatch):
+    """100 000 MAGICC-box members (BASELINE config 4): members with identical parameters give bit-identical series wherever
+    they sit in the grid; the area-weighted four-box temperature warms under the positive forcing; a strided subsample
+    matches the oracle to 1e-9."""
+    torch = pytest.importorskip("torch")
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    M = 100_000
+    b, binds, params, scen = syn.config4(M=M)
+    params = params.copy()
+    params[M // 2:] = params[:M // 2]          # second half repeats the first
+    ens = b.build_ensemble().bind_parameters(binds)
+    ens.select_outputs(["Surface Temperature", "Heat Uptake"], t_start=0, t_stop=351, t_step=25)
+    sc = torch.from_numpy(ens.pack_scenarios(scen)).cuda()
+    p = torch.from_numpy(np.ascontiguousarray(params.T)).cuda()
+    out = torch.empty((ens.output_rows, M), dtype=torch.float64, device="cuda")
+    status = torch.zeros(M, dtype=torch.uint8, device="cuda")
+    ens.run_device(p, sc, out, status, layout=0)
+    torch.cuda.synchronize()
+    assert int(status.max()) == 0
+    assert torch.allclose(out[:, : M // 2], out[:, M // 2:], rtol=0.0, atol=0.0, equal_nan=True)   # NaN at index 0 of pure outputs
+    host = ens.split_outputs(out.cpu().numpy())
+    w = np.array([0.5 * 0.58, 0.5 * 0.42, 0.5 * 0.79, 0.5 * 0.21])
+    t_global = np.einsum("trm,r->tm", host["Surface Temperature"], w)
+    assert np.all(t_global[-1] > t_global[4]) and np.all(t_global[-1] > 0.5) and np.all(t_global[-1] < 12.0)
+    idx = np.arange(0, M, 997)
+    m = oracle_from_builder(b)
+    ref = m.split(m.run_batch(oracle_bindings(b, binds), params[idx], ens.exogenous_names, sc.cpu().numpy(),
+                              ["Surface Temperature", "Heat Uptake"]), ["Surface Temperature", "Heat Uptake"])
+    sel = slice(0, 351, 25)
+    assert rel_err(host["Surface Temperature"][..., idx], ref["Surface Temperature"][sel]) <= TOL64
+    assert rel_err(host["Heat Uptake"][..., idx], ref["Heat Uptake"][sel]) <= TOL64
+
+
+def test_full_size_config5_log_posterior_equals_the_formula_on_the_run_output():
+    """1M-member log-posterior (BASELINE config 5): for a subsample, the fused kernel's value equals the Gaussian
+    log-likelihood (likelihood.rs:209-221) evaluated in numpy on the same members' run output plus the uniform log-prior;
+    the device summary (max, argmax, finite count) matches a host reduction of the full vector."""
+    torch = pytest.importorskip("torch")
+    M = 1 << 20
+    b, binds, params, scen = syn.config2(M=M)
+    ens = b.build_ensemble().bind_parameters(binds)
+    sc_host = ens.pack_scenarios(scen)
+    ens.select_outputs(["Surface Temperature"])
+    truth = np.array([[1.1, 0.05, 1.3, 0.7, 8.0, 100.0]])
+    t_true = ens.run(truth, sc_host)[:, 0]
+    obs = syn.config5_observations(t_true, syn.time_axis().values())
+    priors = [(_ffi.PRIOR_UNIFORM, lo, hi) for lo, hi in syn.TWO_LAYER_RANGES.values()]
+    ens.set_target(obs).set_priors(priors)
+    d_p = torch.from_numpy(np.ascontiguousarray(params.T)).cuda()
+    d_s = torch.from_numpy(sc_host).cuda()
+    d_lp = torch.empty(M, dtype=torch.float64, device="cuda")
+    d_sum = torch.zeros(5, dtype=torch.float64, device="cuda")
+    ens.log_posterior_device(d_p, d_s, d_lp, d_sum, layout=0)
+    torch.cuda.synchronize()
+    lp = d_lp.cpu().numpy()
+    idx = np.arange(0, M, 4099)
+    series = ens.run(params[idx], sc_host)                                  # [351, n]
+    years = syn.time_axis().values()
+    ti = np.array([int(np.where(years == y)[0][0]) for _, y, _, _ in obs])
+    val = np.array([v for _, _, v, _ in obs])[:, None]
+    sig = np.array([s for _, _, _, s in obs])[:, None]
+    loglik = np.sum(-0.5 * ((series[ti] - val) / sig) ** 2, axis=0)
+    logprior = sum(-np.log(hi - lo) for lo, hi in syn.TWO_LAYER_RANGES.values())
+    want = loglik + logprior
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(lp[idx]), fin) and np.max(np.abs(lp[idx][fin] - want[fin]) / np.abs(want[fin])) <= 1e-9
+    summ = np.frombuffer(d_sum.cpu().numpy().tobytes(), dtype=np.dtype([("max", "f8"), ("argmax", "i8"), ("sum", "f8"), ("nfin", "i8"), ("n", "i8")]))[0]
+    finite = np.isfinite(lp)
+    assert summ["n"] == M and summ["nfin"] == finite.sum() and summ["max"] == lp[finite].max() and lp[summ["argmax"]] == summ["max"]
+    assert abs(summ["sum"] - lp[finite].sum()) <= 1e-9 * abs(lp[finite].sum())
