@@ -11,8 +11,8 @@
 //   * a first pass finds the count, minimum and maximum key: members of one ensemble share sign and most exponent bits,
 //     so the digits start after the common prefix of min and max (registers and shuffles only, no atomics);
 //   * targets that share a key prefix form a group with one 2048-bin shared-memory histogram of the next 11 key bits;
-//     a pass streams the segment once, finds each element's group by comparing against the (sorted, <= 10) group
-//     prefixes held in registers and adds to its histogram with warp-aggregated atomics;
+//     a pass streams the segment once, finds each element's group with one lookup in a 2048-entry table keyed by
+//     the low bits of the prefix (most elements miss every group) and adds to its histogram with shared-memory atomics;
 //   * a group whose bin holds <= Q_CAP elements switches to collecting them into shared memory, where the wanted ranks
 //     are picked by counting — for smooth data that is the third pass (11 bits narrow 262 144 members to a few hundred);
 //   * NaNs are excluded (numpy.nanquantile semantics); an all-NaN segment gives NaN.
@@ -57,7 +57,7 @@ struct QShared {
     unsigned long long gprefix[QT_MAX];
     unsigned gcount[QT_MAX], gfill[QT_MAX];
     int gbeg[QT_MAX], gend[QT_MAX];
-    int ngroups, bits, any_hist, pending;
+    int ngroups, bits, pending;
     // targets (order statistics), sorted by rank
     long long trank[QT_MAX];         // rank within the group's prefix
     unsigned long long tkey[QT_MAX]; // result key
@@ -173,7 +173,6 @@ __global__ void __launch_bounds__(Q_THREADS, 1) member_quantiles_kernel(const QA
         sh.gfill[0] = 0u;
         sh.bits = common;
         sh.pending = common == 64 ? 0 : nt;
-        sh.any_hist = n > Q_CAP;
     }
     __syncthreads();
 
