@@ -97,6 +97,13 @@ typedef enum { RSCM_B200_SRC_EXOGENOUS = 0, RSCM_B200_SRC_OWN_STATE = 1, RSCM_B2
  *   FOUR_BOX_OHU, OCEAN_SURFACE_PP, CO2_BUDGET, TERRESTRIAL_CARBON, CH4_CHEMISTRY, N2O_CHEMISTRY:
  *                  the fields of the reference's parameter struct in declaration order, arrays
  *                  expanded, booleans as 0/1 (rscm_b200/components.py, rscm_b200/magicc.py)
+ *   OCEAN_CARBON : model id (0 3D-GFDL, 1 2D-BERN, 2 HILDA), co2_pi, pco2_pi, gas_exchange_scale,
+ *                  gas_exchange_tau, temp_sensitivity, irf_scale, mixed_layer_depth, ocean_surface_area,
+ *                  sst_pi, steps_per_year, max_history_months, irf_switch_time, then irf_early and
+ *                  irf_late as {kind (0 Polynomial, 1 ExponentialSum), n terms, 8 coefficients,
+ *                  8 timescales}, delta_ospp_offsets[5], delta_ospp_coefficients[5],
+ *                  enable_temp_feedback (60 values)
+ *   HALOCARBON_CHEMISTRY: see the enum above (293 values)
  */
 typedef struct {
     int32_t kind;     /* rscm_b200_component_kind */

@@ -161,7 +161,7 @@ class OceanCarbonBuilder:
 
     ``from_parameters({"model": "3D-GFDL" | "2D-BERN" | "HILDA", ...overrides})``; ``irf_early`` / ``irf_late`` may be given as the
     reference's tagged dicts ``{"type": "Polynomial", "coefficients": [...]}`` / ``{"type": "ExponentialSum", "coefficients": [...],
-    "timescales": [...]}`` (at most 8 terms).  The flattened block layout is documented in oracle/magicc_ocean.c."""
+    "timescales": [...]}`` (at most 8 terms).  The flattened block layout is documented in include/rscm_b200.h."""
 
     TYPE_NAME = "OceanCarbon"
     _OSPP_OFF = [1.5568, 7.4706, 1.2748, 2.4491, 1.5468]
