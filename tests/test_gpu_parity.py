@@ -533,3 +533,23 @@ def test_full_size_config5_log_posterior_equals_the_formula_on_the_run_output():
     finite = np.isfinite(lp)
     assert summ["n"] == M and summ["nfin"] == finite.sum() and summ["max"] == lp[finite].max() and lp[summ["argmax"]] == summ["max"]
     assert abs(summ["sum"] - lp[finite].sum()) <= 1e-9 * abs(lp[finite].sum())
+
+
+@pytest.mark.parametrize("step_size", [1.0 / 120.0, 0.05, 0.1, 0.25, 1.0])
+def test_carbon_cycle_collapsed_substeps_match_stepping_over_wide_ranges(step_size):
+    """The device composes the carbon cycle's n RK4 sub-steps analytically (components.cuh); the oracle steps them one by
+    one as the reference does.  Wide ranges: lifetimes from 2 to 200 years, warm and cold feedback (negative alpha*T
+    included), sub-step sizes from 1/120 to 1 year (z = h/lifetime up to ~0.8), emissions with sign changes, non-annual
+    steps (odd sub-step counts)."""
+    values = np.concatenate([np.arange(1750.0, 1900.0), np.arange(1900.0, 2101.0, 3.0)])
+    axis = TimeAxis.from_values(values)
+    b = (ModelBuilder().with_time_axis(axis)
+         .with_rust_component(CarbonCycleBuilder.from_parameters({"tau": 20.3, "conc_pi": 280.0, "alpha_temperature": 0.05})
+                              .with_solver_options(step_size).build())
+         .with_initial_values({"Cumulative Land Uptake": 0.0, "Cumulative Emissions|CO2": 0.0, "Atmospheric Concentration|CO2": 280.0}))
+    t = values - 1750.0
+    scen = [{"Emissions|CO2|Anthropogenic": 0.03 * t * np.cos(t / 40.0) * f, "Surface Temperature": 0.012 * t * f - 1.0} for f in (1.0, 2.5)]
+    binds = {"tau": "CarbonCycle.tau", "alpha": "CarbonCycle.alpha_temperature", "c0": "initial:Atmospheric Concentration|CO2"}
+    params = syn.uniform_params({"tau": (2.0, 200.0), "alpha": (-0.2, 0.4), "c0": (200.0, 500.0)}, 192, 17)
+    got, _, worst, _ = gpu_vs_oracle(b, binds, params, scen)
+    assert worst <= 1e-11 and np.isfinite(got["Atmospheric Concentration|CO2"]).all()
