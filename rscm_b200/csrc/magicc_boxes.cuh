@@ -209,7 +209,27 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     R acc[MAXS];
 #pragma unroll
     for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
-    for (int i = 0; i < n_old; ++i) {
+    // History in chunks of 16 months: sixteen independent (coalesced, member-interleaved) flux loads in flight instead of
+    // one per iteration, and the IRF lags of a chunk form one sliding window of 15 + steps values (uniform loads) instead
+    // of steps loads per month.  Same accumulation order (oldest flux first) as the month-by-month loop.
+    constexpr int CH = 16;
+    int i = 0;
+    for (; i + CH <= n_old; i += CH) {
+        R f[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) f[u] = R(hist[static_cast<long long>(i + u) * cx.runs]);
+        const double *wb = irf + (n_old - i - (CH - 1)); // wb[k]: lag n_old - i - (CH - 1) + k
+        R wv[CH - 1 + MAXS];
+#pragma unroll
+        for (int k = 0; k < CH - 1 + MAXS; ++k)
+            if (k < CH - 1 + steps) wv[k] = R(__ldg(wb + k));
+#pragma unroll
+        for (int u = 0; u < CH; ++u)
+#pragma unroll
+            for (int m = 0; m < MAXS; ++m)
+                if (m < steps) acc[m] += f[u] * wv[(CH - 1 - u) + m];
+    }
+    for (; i < n_old; ++i) {
         const R f = R(hist[static_cast<long long>(i) * cx.runs]);
         const double *w = irf + (n_old - i);
 #pragma unroll
