@@ -81,6 +81,40 @@ SCENARIOS = {  # tolerances exactly as in tests/regression/test_ocean_udeb.py:22
 }
 
 
+# scenarios 08, 10, 12 use the full default configuration and a single tolerance (assert_allclose_recorded, rtol 0.1,
+# atol 1e-6): tests/regression/test_ocean_udeb.py:316-562.  08 is the ABRUPT-2XCO2 step over ten years, 10 and 12 ramp
+# the forcing along the 1pctCO2 pathway; 12 adds efficacy_apply = 2.
+FULL_DEFAULT_SCENARIOS = {"08_sst_to_sat": "step", "10_full_default": "1pctco2", "12_efficacy_ar6_1pctco2": "1pctco2"}
+
+
+def full_default_case(name):
+    years, expected = GOLDEN[name + "/years"], GOLDEN[name + "/temp"]
+    config = json.loads(str(GOLDEN[name + "/config"]))
+    rf = config.get("core_delq2xco2", 3.71)
+    if FULL_DEFAULT_SCENARIOS[name] == "step":
+        erf = np.where(years >= 1851.0, rf, 0.0)   # construct_step_forcing, test_ocean_udeb.py:113-130
+    else:
+        dt = years - config.get("startyear", 1850)
+        erf = rf * np.log(np.where(dt > 0, 1.01 ** dt, 1.0)) / np.log(2.0)
+    params = {"ecs": config.get("core_climatesensitivity", 3.0), "rf_2xco2": rf}
+    if name.startswith("12"):
+        params["efficacy_apply"] = config.get("rf_efficacy_apply", 2)
+    return years, erf, params, expected
+
+
+def recorded_rel_err(actual, expected, atol=1e-6):
+    # assert_allclose_recorded — tests/regression/helpers.py:338-365
+    return float(np.max(np.abs(np.where(np.abs(expected) > atol, (actual - expected) / np.where(expected == 0, 1, expected), 0.0))))
+
+
+@pytest.mark.parametrize("name", sorted(FULL_DEFAULT_SCENARIOS))
+def test_oracle_matches_magicc7_golden_full_default(name):
+    years, erf, params, expected = full_default_case(name)
+    actual = oracle_from_builder(udeb_builder(params, years, erf)).run()["Surface Temperature"] @ AREA_W
+    np.testing.assert_allclose(actual, expected, rtol=0.1, atol=1e-6, err_msg=name)
+    print(name, "max relative error vs MAGICC7: %.3f" % recorded_rel_err(actual, expected))
+
+
 @pytest.mark.parametrize("name", sorted(SCENARIOS))
 def test_oracle_matches_magicc7_golden(name):
     years, expected = GOLDEN[name + "/years"], GOLDEN[name + "/temp"]
@@ -173,3 +207,15 @@ def test_gpu_matches_magicc7_golden(name, tmp_path, monkeypatch):
     actual = t4 @ AREA_W
     for phase, (err, tol) in phased(actual, expected, **SCENARIOS[name]).items():
         assert err <= tol, f"{name} {phase}: {err:.4f} > {tol}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FULL_DEFAULT_SCENARIOS))
+def test_gpu_matches_magicc7_golden_full_default(name, tmp_path, monkeypatch):
+    """Scenarios 08 / 10 / 12 (full default MAGICC7 configuration) with the fused kernel producing the series."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    years, erf, params, expected = full_default_case(name)
+    model = udeb_builder(params, years, erf).build()
+    model.run()
+    t4 = np.asarray(model.timeseries().get_fourbox_timeseries_by_name("Surface Temperature").values())
+    np.testing.assert_allclose(t4 @ AREA_W, expected, rtol=0.1, atol=1e-6, err_msg=name)
