@@ -208,6 +208,8 @@ int rscm_b200_time_index(const rscm_b200_ensemble *h, double time);
  * "initial:<variable name>".  A column may appear several times (e.g. conc_pi of
  * CarbonCycle and CO2ERF).  Unbound slots keep the graph description's value.
  */
+/* Rebinding with a different n_columns drops priors set for the previous binding
+ * (they are per column): call rscm_b200_set_priors again. */
 int rscm_b200_bind_parameters(rscm_b200_ensemble *h, int n_bindings, const char *const *slots,
                               const int32_t *columns, int n_columns);
 
@@ -230,6 +232,13 @@ int64_t rscm_b200_output_rows(const rscm_b200_ensemble *h);
  *            bit1 = a non-finite value was produced; may be NULL
  * All pointers are DEVICE pointers; work is enqueued on `stream`
  * (a cudaStream_t, NULL = default stream) and is asynchronous.
+ * Streams: the handle's staged scenario table, scratch and summary buffers are
+ * per handle, so the engine orders launches itself: a launch on a stream other
+ * than the previous launch's first waits (cudaStreamWaitEvent) for the previous
+ * launch's kernel.  Calls on different streams, and device calls followed by the
+ * host entry points (which use internal non-blocking streams), are therefore safe
+ * but do not overlap each other; the CALLER's buffers (params, scenarios, out)
+ * must still not be reused before the work that reads/writes them has finished.
  */
 int rscm_b200_run_device(rscm_b200_ensemble *h, const double *params, int64_t M, int params_layout,
                          const double *scenarios, int64_t S, double *out, uint8_t *status,

@@ -775,6 +775,12 @@ class Ensemble:
         runs = max(S, 1) * M
         if out is None:
             out = np.empty((self.output_rows, runs))
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.flags.writeable
+                  and out.shape == (self.output_rows, runs)):
+            raise ValueError(f"out must be a writable C-contiguous float64 array of shape ({self.output_rows}, {runs})")
+        if status is not None and not (isinstance(status, np.ndarray) and status.dtype == np.uint8 and status.flags.c_contiguous
+                                       and status.flags.writeable and status.size == runs):
+            raise ValueError(f"status must be a writable C-contiguous uint8 array of {runs} elements")
         _ffi.check(
             _ffi.lib.rscm_b200_run_host(self._h, self._ptr(p), M, layout, self._ptr(sc), S, self._ptr(out), self._ptr(status)),
             self._h,

@@ -114,6 +114,12 @@ struct rscm_b200_ensemble {
     rscm_dev::SummaryDev *d_summary = nullptr;
     int64_t cap_params = 0, cap_out = 0, cap_status = 0, cap_scen = 0, cap_logpost = 0;
 
+    // ordering between launches of this handle on different streams: d_exo, the scratch slots, the summary partials and
+    // the ticket are per handle, so a launch on another stream first waits for the previous launch's kernel
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
+
     // stats
     int64_t launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -194,8 +200,11 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     if (h->n_cols > 0 && !d_params) return fail(h, RSCM_B200_EINVAL, "parameter matrix required (columns are bound)");
     if (logp && !h->has_target) return fail(h, RSCM_B200_EINVAL, "set a target before evaluating the log-posterior");
 
+    if (h->has_last && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->last_done, 0));
+
     if (g.n_exo_rows > 0) {
         if (S > h->exo_capacity_S) {
+            if (h->has_last) CU(cudaEventSynchronize(h->last_done)); // the old table may still be read
             if (h->d_exo) cudaFree(h->d_exo);
             h->d_exo = nullptr;
             CU(cudaMalloc(&h->d_exo, static_cast<size_t>(S) * g.n_exo_rows * h->Tpad * 8));
@@ -230,7 +239,7 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
         const int64_t need = static_cast<int64_t>(g.n_scratch_rows) * S * M;
         const int slot = (st == h->streams[1] && st) ? 1 : 0;
         if (need > h->cap_scratch[slot]) {
-            if (h->d_scratch[slot]) cudaFree(h->d_scratch[slot]);
+            if (h->d_scratch[slot]) cudaFree(h->d_scratch[slot]); // (cudaFree synchronises the device)
             h->d_scratch[slot] = nullptr;
             h->cap_scratch[slot] = 0;
             CU(cudaMalloc(&h->d_scratch[slot], static_cast<size_t>(need) * 8));
@@ -308,6 +317,9 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     }
     CU(cudaEventRecord(h->events[ei].second, st));
     h->ev_pending[ei] = 1;
+    h->last_done = h->events[ei].second;
+    h->last_stream = st;
+    h->has_last = true;
     h->launches++;
     return RSCM_B200_OK;
 }
@@ -528,6 +540,12 @@ int rscm_b200_bind_parameters(rscm_b200_ensemble *h, int n_bindings, const char 
     }
     h->slot_col = slot_col;
     h->init_col = init_col;
+    if (n_columns != h->n_cols && h->n_priors > 0) {
+        // the priors were given per column of the previous binding: a different column count invalidates them
+        if (h->d_priors) cudaFree(h->d_priors);
+        h->d_priors = nullptr;
+        h->n_priors = 0;
+    }
     h->n_cols = n_columns;
     return RSCM_B200_OK;
 }

@@ -669,9 +669,22 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
     };
     if (d.n_aggregates > 0 && !d.has_schema) { err = "aggregates require a schema"; return false; }
 
+    bool grid_mismatch = false;
+    std::string mismatch_msg;
     auto add_var = [&](const char *name, int grid, int req) {
         int v = g.find_var(name);
-        if (v >= 0) return v; // the first definition wins (model/validation.rs:30-107)
+        if (v >= 0) {
+            // The first definition wins; without a schema a second definition on another grid is an error
+            // (verify_definition, model/validation.rs:30-107: GridTypeMismatch unless has_schema — the schema's relaxed
+            // rules are what allow the read/write aggregation transforms).
+            if (!d.has_schema && g.vars[v].grid != grid && !grid_mismatch) {
+                static const char *const GN[] = {"Scalar", "FourBox", "Hemispheric"};
+                grid_mismatch = true;
+                mismatch_msg = std::string("grid type mismatch for variable '") + name + "': defined on " + GN[g.vars[v].grid] +
+                               ", redefined on " + GN[grid] + " (a VariableSchema is required for grid aggregation)";
+            }
+            return v;
+        }
         Variable var;
         var.name = name;
         var.grid = grid;
@@ -735,6 +748,7 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         g.nodes.push_back(n);
     }
     g.n_user = d.n_components;
+    if (grid_mismatch) { err = mismatch_msg; return false; }
 
     for (int i = 0; i < d.n_unit_factors; ++i) {
         const rscm_b200_unit_factor &uf = d.unit_factors[i];
