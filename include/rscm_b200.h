@@ -42,6 +42,7 @@ extern "C" {
 #define RSCM_B200_ENODEVICE (-3)    /* no usable CUDA device */
 #define RSCM_B200_ECUDA (-4)        /* CUDA runtime error */
 #define RSCM_B200_ENOMEM (-5)
+#define RSCM_B200_ECOMM (-6)        /* NCCL / peer-memory error (multi-GPU entry points) */
 
 /* Component kinds.  Replaces `Arc<dyn Component>` objects added through
  * ModelBuilder::with_component (crates/rscm-core/src/model/builder.rs:45-60);
@@ -333,6 +334,86 @@ int rscm_b200_stretch_propose(const double *d_positions, int64_t ld, int n_cols,
 int rscm_b200_stretch_accept(double *d_positions, int64_t ld, int n_cols, int64_t active_begin, int64_t n_active,
                              const double *d_proposals, int64_t ld_proposals, const double *d_z, const double *d_logpost_new,
                              double *d_logpost, uint64_t seed, uint32_t step, unsigned long long *d_n_accepted, void *stream);
+
+/* ---- multi-GPU: member sharding and the all-gather of per-member log-posteriors ----
+ * The path shards by member: ModelRunner::run_batch maps `run` over independent
+ * rows (crates/rscm-calibrate/src/model_runner.rs:261-266, rayon par_iter), and
+ * EnsembleSampler::log_posterior_batch (sampler/ensemble.rs:143-178) needs every
+ * member's log-posterior on the host that advances the walkers.  One process per
+ * GPU; rank r owns members [r*M/G, (r+1)*M/G) (rscm_b200_comm_shard).  The only
+ * exchange is 8 bytes per member.  A communicator wraps an NCCL communicator
+ * (libnccl.so.2 is loaded at run time: RSCM_B200_NCCL_LIB, else the copy already
+ * mapped into the process, else the system's) plus, when the GPUs can map each
+ * other's memory (CUDA IPC over NVLink / NVSwitch), a table of peer pointers for
+ * buffers obtained from rscm_b200_comm_symmetric_alloc.
+ *
+ * Set-up mirrors ncclGetUniqueId / ncclCommInitRank: rank 0 calls
+ * rscm_b200_comm_unique_id, the host distributes the 128 bytes by its own means
+ * (MPI, a file, torch.distributed's store), every rank calls rscm_b200_comm_init.
+ * All of comm_init, comm_symmetric_alloc, allgather_f64, logpost_sharded_device and
+ * sampler_iterate are COLLECTIVE: every rank must call them in the same order.
+ */
+#define RSCM_B200_UNIQUE_ID_BYTES 128
+typedef struct rscm_b200_comm rscm_b200_comm;
+
+int rscm_b200_comm_unique_id(void *unique_id /* RSCM_B200_UNIQUE_ID_BYTES */);
+/* device: CUDA ordinal of this rank's GPU (-1 = current).  world = 1 needs no NCCL and no unique id. */
+int rscm_b200_comm_init(const void *unique_id, int rank, int world, int device, rscm_b200_comm **out);
+void rscm_b200_comm_destroy(rscm_b200_comm *c);
+const char *rscm_b200_comm_last_error(const rscm_b200_comm *c);
+int rscm_b200_comm_rank(const rscm_b200_comm *c);
+int rscm_b200_comm_world(const rscm_b200_comm *c);
+/* 1 when symmetric buffers are mapped into every peer (the fused all-gather is available), else 0 (NCCL only;
+ * RSCM_B200_NO_P2P=1 forces this) */
+int rscm_b200_comm_peer_access(const rscm_b200_comm *c);
+/* member block of this rank: [begin, end) = [rank*M/world, (rank+1)*M/world) */
+int rscm_b200_comm_shard(const rscm_b200_comm *c, int64_t M, int64_t *begin, int64_t *end);
+/* `bytes` of zeroed device memory that every peer can store into (freed with the communicator) */
+int rscm_b200_comm_symmetric_alloc(rscm_b200_comm *c, size_t bytes, void **d_ptr);
+/* ncclAllGather of n_local doubles per rank: d_global[r*n_local + i] = rank r's d_local[i].  Device pointers;
+ * in place when d_local == d_global + rank*n_local.  Replaces the rayon join at the end of run_batch. */
+int rscm_b200_allgather_f64(rscm_b200_comm *c, const double *d_local, int64_t n_local, double *d_global, void *stream);
+/* log_posterior_batch over G GPUs.  `params` is the GLOBAL matrix ([n_columns][M] layout 0 or [M][n_columns]
+ * layout 1), identical on every rank; each rank evaluates its member block in place (no copy of the block: the kernel
+ * takes the offset and the global leading dimension) and all ranks end up with all S*M log-posteriors in
+ * logpost_global[s*M + m].  When logpost_global lies in symmetric memory and peers are mapped, ONE kernel does both:
+ * it stores each member's 8 bytes into every peer's buffer over NVLink as the member finishes and its last block raises
+ * a flag in every peer; a one-warp kernel then waits for all flags.  Otherwise the kernel is followed by ncclAllGather
+ * (equal blocks, S = 1) or grouped ncclBroadcasts, in place.  Asynchronous on `stream`.
+ * With the fused path consecutive calls must alternate between two destination buffers (a peer may still be reading
+ * the previous result while this rank's next evaluation stores into it). */
+int rscm_b200_logpost_sharded_device(rscm_b200_ensemble *h, rscm_b200_comm *c, const double *params, int64_t M, int params_layout,
+                                     const double *scenarios, int64_t S, double *logpost_global, void *stream);
+/* synchronous health check of the fused path: RSCM_B200_ECOMM if a peer missed a rendezvous (20 s timeout on the device) */
+int rscm_b200_comm_check(rscm_b200_comm *c);
+
+/* Walker state of the stretch-move sampler, all DEVICE pointers, replicated on every rank
+ * (EnsembleSampler::run, sampler/ensemble.rs:412-487; SamplerState, sampler/state.rs). */
+typedef struct {
+    double *positions;       /* [n_cols][ld] SoA */
+    int64_t ld;
+    int32_t n_cols;
+    int32_t reserved;
+    int64_t n_walkers;       /* even */
+    double *logpost;         /* [n_walkers] current log-posterior of every walker */
+    double *proposals;       /* [n_cols][n_walkers/2] scratch */
+    double *z;               /* [n_walkers/2] scratch */
+    double *logpost_new[2];  /* [n_walkers/2] each, one per half-update; symmetric memory enables the fused all-gather */
+    unsigned long long *n_accepted; /* running count of accepted moves, may be NULL */
+    double a;                /* stretch parameter (> 1) */
+    uint64_t seed;
+    uint32_t first_iteration; /* iteration number of the first iteration of this call (keys the random stream) */
+    uint32_t thin;           /* chain recording: after iteration i with i % thin == 0 ... (0 = no recording) */
+    double *chain_positions; /* ... positions are copied to chain_positions[(i/thin)][n_cols][n_walkers] */
+    double *chain_logpost;   /* ... and logpost to chain_logpost[(i/thin)][n_walkers] (Chain::push, sampler/chain.rs:63) */
+    int64_t chain_capacity;  /* kept samples the two chain buffers can hold */
+} rscm_b200_sampler_state;
+/* n_iterations of EnsembleSampler::update (sampler/ensemble.rs:489-546): per half-ensemble propose -> sharded fused
+ * log-posterior (+ all-gather) -> accept/reject, enqueued on `stream` without host synchronisation.  The first iteration
+ * of a call runs eagerly; with use_graph != 0 the remaining ones replay ONE captured CUDA graph (the iteration number is a
+ * device-side counter), so the host cost per iteration is a single graph launch.  Target and priors must be set. */
+int rscm_b200_sampler_iterate(rscm_b200_ensemble *h, rscm_b200_comm *c, const rscm_b200_sampler_state *state, const double *scenarios,
+                              int64_t S, int n_iterations, int use_graph, void *stream);
 
 /* ---- ensemble summaries on the device -----------------------------------------
  * Quantiles across members of an output block d_out[rows][S*M] (the layout of

@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(_HERE, "librscm_b200.so")
 ABI_VERSION = 1
 
 OK = 0
-EINVAL, EUNSUPPORTED, ENODEVICE, ECUDA, ENOMEM = -1, -2, -3, -4, -5
+EINVAL, EUNSUPPORTED, ENODEVICE, ECUDA, ENOMEM, ECOMM = -1, -2, -3, -4, -5, -6
+UNIQUE_ID_BYTES = 128
 
 # component kinds
 TWO_LAYER, CARBON_CYCLE, CO2_ERF, GHG_FORCING = 1, 2, 3, 5
@@ -110,6 +111,15 @@ class LogpostSummary(C.Structure):
     ]
 
 
+class SamplerState(C.Structure):
+    _fields_ = [
+        ("positions", C.c_void_p), ("ld", C.c_int64), ("n_cols", C.c_int32), ("reserved", C.c_int32), ("n_walkers", C.c_int64),
+        ("logpost", C.c_void_p), ("proposals", C.c_void_p), ("z", C.c_void_p), ("logpost_new", C.c_void_p * 2),
+        ("n_accepted", C.c_void_p), ("a", C.c_double), ("seed", C.c_uint64), ("first_iteration", C.c_uint32), ("thin", C.c_uint32),
+        ("chain_positions", C.c_void_p), ("chain_logpost", C.c_void_p), ("chain_capacity", C.c_int64),
+    ]
+
+
 # every symbol include/rscm_b200.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 _PD = C.c_void_p  # double* passed as integer addresses (host numpy or device data_ptr)
@@ -146,6 +156,19 @@ SYMBOLS = {
     "rscm_b200_kernel_ms": (C.c_double, [_H, C.c_int]),
     "rscm_b200_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "rscm_b200_member_quantiles": (C.c_int, [_PD, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.c_int, _PD, C.c_void_p]),
+    "rscm_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "rscm_b200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
+    "rscm_b200_comm_destroy": (None, [_H]),
+    "rscm_b200_comm_last_error": (C.c_char_p, [_H]),
+    "rscm_b200_comm_rank": (C.c_int, [_H]),
+    "rscm_b200_comm_world": (C.c_int, [_H]),
+    "rscm_b200_comm_peer_access": (C.c_int, [_H]),
+    "rscm_b200_comm_shard": (C.c_int, [_H, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "rscm_b200_comm_symmetric_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rscm_b200_allgather_f64": (C.c_int, [_H, _PD, C.c_int64, _PD, C.c_void_p]),
+    "rscm_b200_logpost_sharded_device": (C.c_int, [_H, _H, _PD, C.c_int64, C.c_int, _PD, C.c_int64, _PD, C.c_void_p]),
+    "rscm_b200_comm_check": (C.c_int, [_H]),
+    "rscm_b200_sampler_iterate": (C.c_int, [_H, _H, C.POINTER(SamplerState), _PD, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "rscm_b200_stretch_propose": (C.c_int, [_PD, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_uint64,
                                             C.c_uint32, _PD, C.c_int64, _PD, C.c_void_p]),
     "rscm_b200_stretch_accept": (C.c_int, [_PD, C.c_int64, C.c_int, C.c_int64, C.c_int64, _PD, C.c_int64, _PD, _PD, _PD, C.c_uint64,
@@ -183,4 +206,11 @@ def check(code: int, handle=None) -> None:
     if code == OK:
         return
     msg = lib.rscm_b200_last_error(handle) if handle else lib.rscm_b200_last_global_error()
+    raise EngineError(code, (msg or b"").decode("utf-8", "replace"))
+
+
+def check_comm(code: int, comm=None) -> None:
+    if code == OK:
+        return
+    msg = lib.rscm_b200_comm_last_error(comm) if comm else lib.rscm_b200_last_global_error()
     raise EngineError(code, (msg or b"").decode("utf-8", "replace"))

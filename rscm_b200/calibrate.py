@@ -468,12 +468,14 @@ class EnsembleSampler:
 class DeviceEnsembleSampler(EnsembleSampler):
     """The same Goodman & Weare loop with nothing but the chain leaving the GPU.
 
-    Walker positions ``[n_params][n_walkers]``, proposals, stretch factors and log-posteriors stay in HBM; one iteration is
-    two (``stretch_propose`` -> fused log-posterior kernel -> ``stretch_accept``) triples on one stream
-    (include/rscm_b200.h; sampler/ensemble.rs:489-546, sampler/moves.rs:55-125).  Random draws are Philox4x32-10
-    functions of (seed, walker, step, purpose), so a run is reproducible from ``seed`` and, under ``torch.distributed``,
-    every rank keeps an identical replica of the walker state: each rank evaluates its member block of the active half and
-    the log-posteriors are all-gathered (rscm_b200/dist.py) — no other exchange.
+    Walker positions ``[n_params][n_walkers]``, proposals, stretch factors and log-posteriors stay in HBM and the loop itself
+    runs behind the C ABI (``rscm_b200_sampler_iterate``, include/rscm_b200.h; sampler/ensemble.rs:489-546,
+    sampler/moves.rs:55-125): per half-update ``stretch_propose`` -> fused log-posterior kernel -> ``stretch_accept`` on one
+    stream, each iteration replayed from one CUDA graph.  Random draws are Philox4x32-10 functions of (seed, walker, step,
+    purpose), so a run is reproducible from ``seed`` and, with several ranks, every rank keeps an identical replica of the
+    walker state: each rank evaluates its member block of the active half in place and the 8-byte log-posteriors are
+    all-gathered — stored straight into every peer's buffer by the log-posterior kernel when the GPUs map each other's
+    memory (``collective == "fused peer stores"``), by NCCL otherwise — no other exchange.
     """
 
     MAX_DEVICE_CHAIN_BYTES = 4 << 30
@@ -482,29 +484,24 @@ class DeviceEnsembleSampler(EnsembleSampler):
         import torch
         return int(torch.cuda.current_stream().cuda_stream)
 
-    def _evaluate(self, d_params, d_out, n, dist_group):
-        """log-posterior of the n parameter sets in d_params [n_params][n] into d_out [n]."""
-        import torch
-        ens, scen = self.runner.ensemble, self._d_scen
-        S = 0 if scen is None else 1
-        if dist_group is None:
-            ens.log_posterior_device(d_params, scen, d_out, layout=0, M=n, S=S, stream=self._stream())
-            return
-        import torch.distributed as dist
-        from .dist import allgather_members, member_shard
-        g = None if dist_group is True else dist_group
-        world = dist.get_world_size(g)
-        lo, hi = member_shard(n, dist.get_rank(g), world)
-        local = torch.empty(hi - lo, dtype=torch.float64, device=d_params.device)
-        if hi > lo:
-            ens.log_posterior_device(d_params[:, lo:hi].contiguous(), scen, local, layout=0, M=hi - lo, S=S, stream=self._stream())
-        if n % world == 0:
-            dist.all_gather_into_tensor(d_out, local, group=g)   # equal contiguous shards: gathered straight into place
-        else:
-            d_out.copy_(allgather_members(local, n, g))
+    def _comm(self, distributed):
+        """``distributed``: False / None (one GPU), True (torch.distributed's default group), a process group, or a
+        :class:`rscm_b200.dist.Comm`."""
+        from .dist import Comm
+        if isinstance(distributed, Comm):
+            return distributed
+        key = "single" if not distributed else ("world" if distributed is True else id(distributed))
+        cache = self.__dict__.setdefault("_comms", {})
+        if key not in cache:
+            import torch
+            dev = torch.cuda.current_device()
+            cache[key] = Comm.single(dev) if not distributed else Comm.from_torch(None if distributed is True else distributed, dev)
+        return cache[key]
 
     def run(self, n_iterations: int, init: WalkerInit, thin: int = 1, n_walkers: int | None = None, progress=None, *,
-            seed: int | None = None, distributed: bool | object = False) -> Chain:
+            seed: int | None = None, distributed: bool | object = False, use_graph: bool = True) -> Chain:
+        import ctypes as C
+
         import torch
 
         W = n_walkers or self._default_n_walkers
@@ -515,25 +512,34 @@ class DeviceEnsembleSampler(EnsembleSampler):
         scen = self.runner._scenarios
         if scen is not None and scen.shape[0] != 1:
             raise ValueError("the sampler evaluates one scenario per walker; the runner holds %d" % scen.shape[0])
-        group = (True if distributed is True else distributed) if distributed else None
+        comm = self._comm(distributed)
         dev = torch.device("cuda", torch.cuda.current_device())
-        self._d_scen = None if scen is None else torch.from_numpy(np.ascontiguousarray(scen)).to(dev)
+        d_scen = None if scen is None else torch.from_numpy(np.ascontiguousarray(scen)).to(dev)
+        S = 0 if d_scen is None else 1
         P, half, thin = len(self.params), W // 2, max(1, int(thin))
         if seed is None:
             seed = int(self._rng.integers(0, 2 ** 63))
         pos0 = torch.from_numpy(np.ascontiguousarray(init.initialize(W, self.params, self._rng).T)).to(dev)  # [P][W]
-        if group is not None:
-            import torch.distributed as dist
-            meta = torch.tensor([seed], dtype=torch.int64, device=dev)
-            dist.broadcast(meta, 0, group=None if group is True else group)   # one seed, one initial ensemble on every rank
-            dist.broadcast(pos0, 0, group=None if group is True else group)
-            seed = int(meta.item())
+        if comm.world > 1:   # one seed, one initial ensemble on every rank
+            box = torch.empty(P * W + 1, dtype=torch.float64, device=dev)
+            box[0] = float(seed % (1 << 52))
+            box[1:] = pos0.reshape(-1)
+            gathered = torch.empty(comm.world * box.numel(), dtype=torch.float64, device=dev)
+            comm.allgather(box, gathered, self._stream())
+            torch.cuda.synchronize()
+            seed = int(gathered[0].item())
+            pos0 = gathered[1:box.numel()].reshape(P, W).clone()
+        ens, lib = self.runner.ensemble, _ffi.lib
         d_pos = pos0.contiguous()
-        d_logp = torch.empty(W, dtype=torch.float64, device=dev)
-        self._evaluate(d_pos, d_logp, W, group)
+        # initial log-posterior of all W walkers (sharded like every later evaluation)
+        key = (id(comm), W)
+        if getattr(self, "_sym_key", None) != key:   # symmetric memory lives as long as the communicator: allocate once per shape
+            self._sym = (comm.symmetric_empty(W), comm.symmetric_empty(half), comm.symmetric_empty(half))
+            self._sym_key = key
+        d_logp, d_lpn0, d_lpn1 = self._sym
+        comm.log_posterior_sharded(ens, d_pos, d_scen, d_logp, M=W, S=S, layout=0, stream=self._stream())
         d_prop = torch.empty((P, half), dtype=torch.float64, device=dev)
         d_z = torch.empty(half, dtype=torch.float64, device=dev)
-        d_lpn = torch.empty(half, dtype=torch.float64, device=dev)
         d_nacc = torch.zeros(1, dtype=torch.int64, device=dev)
         n_keep = (n_iterations + thin - 1) // thin
         on_device = n_keep * W * (P + 1) * 8 <= self.MAX_DEVICE_CHAIN_BYTES
@@ -541,24 +547,32 @@ class DeviceEnsembleSampler(EnsembleSampler):
             d_samples = torch.empty((n_keep, P, W), dtype=torch.float64, device=dev)
             d_logps = torch.empty((n_keep, W), dtype=torch.float64, device=dev)
         chain = Chain(self.params.param_names, thin)
-        lib, ptr = _ffi.lib, (lambda t: t.data_ptr())
-        for it in range(n_iterations):
-            for hidx, (a0, c0) in enumerate(((0, half), (half, 0))):
-                step = 2 * it + hidx
-                _ffi.check(lib.rscm_b200_stretch_propose(ptr(d_pos), W, P, a0, half, c0, half, self.a, seed, step, ptr(d_prop), half,
-                                                         ptr(d_z), self._stream()))
-                self._evaluate(d_prop, d_lpn, half, group)
-                _ffi.check(lib.rscm_b200_stretch_accept(ptr(d_pos), W, P, a0, half, ptr(d_prop), half, ptr(d_z), ptr(d_lpn), ptr(d_logp),
-                                                        seed, step, ptr(d_nacc), self._stream()))
-            if it % thin == 0:
-                if on_device:
-                    d_samples[it // thin].copy_(d_pos)
-                    d_logps[it // thin].copy_(d_logp)
-                else:
+        st = _ffi.SamplerState()
+        st.positions, st.ld, st.n_cols, st.n_walkers = d_pos.data_ptr(), W, P, W
+        st.logpost, st.proposals, st.z = d_logp.data_ptr(), d_prop.data_ptr(), d_z.data_ptr()
+        st.logpost_new[0], st.logpost_new[1] = d_lpn0.data_ptr(), d_lpn1.data_ptr()
+        st.n_accepted, st.a, st.seed = d_nacc.data_ptr(), self.a, seed
+        sp = 0 if d_scen is None else d_scen.data_ptr()
+
+        if on_device:
+            st.thin, st.chain_positions, st.chain_logpost, st.chain_capacity = thin, d_samples.data_ptr(), d_logps.data_ptr(), n_keep
+
+        def advance(first: int, n: int) -> None:
+            st.first_iteration = first
+            _ffi.check_comm(lib.rscm_b200_sampler_iterate(ens._h, comm._h, C.byref(st), sp, S, n, 1 if use_graph else 0, self._stream()), comm._h)
+
+        if on_device and progress is None:
+            advance(0, n_iterations)      # the whole run is enqueued by one call; kept samples are recorded on the device
+        else:
+            for it in range(n_iterations):
+                advance(it, 1)
+                if not on_device and it % thin == 0:
                     chain._samples.append(d_pos.T.cpu().numpy())
                     chain._log_probs.append(d_logp.cpu().numpy())
-            if progress is not None:  # a host read-back per iteration: only when asked for
-                progress(ProgressInfo(it, n_iterations, int(d_nacc.item()) / ((it + 1) * W), float(d_logp.mean().item())))
+                if progress is not None:  # a host read-back per iteration: only when asked for
+                    progress(ProgressInfo(it, n_iterations, int(d_nacc.item()) / ((it + 1) * W), float(d_logp.mean().item())))
+        torch.cuda.synchronize()
+        comm.check()
         if on_device and n_keep:
             chain._samples = list(d_samples.permute(0, 2, 1).contiguous().cpu().numpy())
             chain._log_probs = list(d_logps.cpu().numpy())
@@ -566,4 +580,5 @@ class DeviceEnsembleSampler(EnsembleSampler):
         self.acceptance_rate = int(d_nacc.item()) / max(1, n_iterations * W)
         self.final_positions = d_pos.T.cpu().numpy()
         self.final_log_probs = d_logp.cpu().numpy()
+        self.collective = None if comm.world == 1 else ("fused peer stores (NVLink)" if comm.peer_access else "ncclAllGather")
         return chain

@@ -5,6 +5,7 @@
 // tools/gen_aot from the same emitter) -> launch the fused member-loop kernel
 // (kernel.cuh).  There is no CPU execution path in this library.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math_constants.h>
 
 #include <algorithm>
@@ -129,6 +130,29 @@ struct rscm_b200_ensemble {
     int64_t kernel_ms_n = 0;
 };
 
+// A communicator over the ranks that share one ensemble evaluation (one process per GPU).  NCCL carries the generic
+// collectives; buffers obtained from rscm_b200_comm_symmetric_alloc are additionally mapped into every peer (CUDA IPC over
+// NVLink / NVSwitch), which is what the fused log-posterior + all-gather kernel stores through.
+struct rscm_b200_comm {
+    void *nccl = nullptr;
+    int rank = 0, world = 1, device = 0;
+    bool p2p = false; // every peer's symmetric memory is mapped here
+    std::string err;
+    struct Segment {
+        void *local = nullptr;
+        size_t bytes = 0;
+        void *peer[rscm_dev::MAX_PEERS] = {};
+    };
+    std::vector<Segment> segments; // segments[0] = control block: flags[MAX_PEERS], epoch, error
+    unsigned long long *flags = nullptr, *d_epoch = nullptr;
+    int *d_error = nullptr;
+    unsigned long long timeout_ns = 20000000000ull;
+    // sampler iteration recorded as a CUDA graph (rscm_b200_sampler_iterate)
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<uintptr_t> graph_key;
+    unsigned *d_iteration = nullptr;
+};
+
 namespace {
 
 int fail(rscm_b200_ensemble *h, int code, const std::string &msg)
@@ -187,10 +211,20 @@ size_t smem_bytes(const rscm_b200_ensemble *h, bool logp)
     return b;
 }
 
+// What a launch that evaluates a member block of a larger ensemble in place needs beyond the plain arguments.
+struct LaunchOpts {
+    int64_t ld_col = 0; // layout 0: leading dimension of the parameter matrix (0 = M)
+    int64_t lp_ld = 0;  // scenario stride of the log-posterior array (0 = M)
+    int n_peers = 0;    // fused all-gather over peer memory (kernel.cuh)
+    double *peer_lp[rscm_dev::MAX_PEERS] = {};
+    unsigned long long *peer_flag[rscm_dev::MAX_PEERS] = {};
+    const unsigned long long *epoch = nullptr;
+};
+
 // enqueue scenario packing + the fused kernel on `st`
 int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout, const double *d_scen, int64_t S,
             double *d_out, unsigned char *d_status, double *d_logpost, rscm_dev::SummaryDev *d_summary, bool write,
-            bool logp, cudaStream_t st, bool pack)
+            bool logp, cudaStream_t st, bool pack, const LaunchOpts *opts = nullptr)
 {
     const rscm::Graph &g = h->g;
     if (M <= 0) return fail(h, RSCM_B200_EINVAL, "M must be positive");
@@ -200,10 +234,16 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     if (h->n_cols > 0 && !d_params) return fail(h, RSCM_B200_EINVAL, "parameter matrix required (columns are bound)");
     if (logp && !h->has_target) return fail(h, RSCM_B200_EINVAL, "set a target before evaluating the log-posterior");
 
-    if (h->has_last && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->last_done, 0));
+    // inside a stream capture (rscm_b200_sampler_iterate records its iteration as a CUDA graph) nothing may allocate,
+    // synchronise or time: the buffers were sized by the eager iteration that precedes every capture
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(st, &cap));
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    if (!capturing && h->has_last && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->last_done, 0));
 
     if (g.n_exo_rows > 0) {
         if (S > h->exo_capacity_S) {
+            if (capturing) return fail(h, RSCM_B200_EINVAL, "scenario table would have to grow inside a stream capture");
             if (h->has_last) CU(cudaEventSynchronize(h->last_done)); // the old table may still be read
             if (h->d_exo) cudaFree(h->d_exo);
             h->d_exo = nullptr;
@@ -224,7 +264,14 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     std::memset(&a, 0, sizeof a);
     a.params = d_params;
     a.M = M;
-    if (layout == 0) { a.ld_col = M; a.ld_mem = 1; } else { a.ld_col = 1; a.ld_mem = h->n_cols; }
+    if (layout == 0) { a.ld_col = (opts && opts->ld_col) ? opts->ld_col : M; a.ld_mem = 1; } else { a.ld_col = 1; a.ld_mem = h->n_cols; }
+    a.lp_ld = (opts && opts->lp_ld) ? opts->lp_ld : M;
+    if (opts && opts->n_peers > 0) {
+        a.n_peers = opts->n_peers;
+        for (int p = 0; p < opts->n_peers; ++p) { a.peer_lp[p] = opts->peer_lp[p]; a.peer_flag[p] = opts->peer_flag[p]; }
+        a.epoch = opts->epoch;
+        a.ticket = h->d_ticket;
+    }
     a.n_cols = h->n_cols;
     a.T = g.T;
     a.Tpad = h->Tpad;
@@ -239,6 +286,7 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
         const int64_t need = static_cast<int64_t>(g.n_scratch_rows) * S * M;
         const int slot = (st == h->streams[1] && st) ? 1 : 0;
         if (need > h->cap_scratch[slot]) {
+            if (capturing) return fail(h, RSCM_B200_EINVAL, "scratch would have to grow inside a stream capture");
             if (h->d_scratch[slot]) cudaFree(h->d_scratch[slot]); // (cudaFree synchronises the device)
             h->d_scratch[slot] = nullptr;
             h->cap_scratch[slot] = 0;
@@ -272,6 +320,7 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     if (logp && d_summary) {
         const int64_t nb = static_cast<int64_t>(grid.x) * grid.y;
         if (nb > h->partials_capacity) {
+            if (capturing) return fail(h, RSCM_B200_EINVAL, "summary partials would have to grow inside a stream capture");
             if (h->d_partials) cudaFree(h->d_partials);
             h->d_partials = nullptr;
             CU(cudaMalloc(&h->d_partials, static_cast<size_t>(nb) * sizeof(rscm_dev::BlockPartial)));
@@ -284,7 +333,9 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
 
     // CUDA-event timing of the fused kernel on its launch stream
     size_t ei = h->ev_next;
-    if (h->events.size() < 64) {
+    if (capturing) {
+        // no timing and no ordering event inside a capture
+    } else if (h->events.size() < 64) {
         cudaEvent_t e0, e1;
         CU(cudaEventCreate(&e0));
         CU(cudaEventCreate(&e1));
@@ -297,8 +348,10 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
             harvest_event(h, ei);
         }
     }
-    h->ev_next = (ei + 1) % 64;
-    CU(cudaEventRecord(h->events[ei].first, st));
+    if (!capturing) {
+        h->ev_next = (ei + 1) % 64;
+        CU(cudaEventRecord(h->events[ei].first, st));
+    }
     if (h->use_jit) {
         const int variant = (write && !logp) ? 0 : ((!write && logp) ? 1 : 2);
         if (!h->jit.fn[variant]) { // first use of this kernel variant: compile (disk-cached) and load it
@@ -315,13 +368,60 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
         cudaError_t e = h->prog->launch(h->dtype, write, logp, grid, smem_bytes(h, logp), st, a);
         if (e != cudaSuccess) return fail(h, RSCM_B200_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     }
-    CU(cudaEventRecord(h->events[ei].second, st));
-    h->ev_pending[ei] = 1;
-    h->last_done = h->events[ei].second;
-    h->last_stream = st;
-    h->has_last = true;
+    if (!capturing) {
+        CU(cudaEventRecord(h->events[ei].second, st));
+        h->ev_pending[ei] = 1;
+        h->last_done = h->events[ei].second;
+        h->last_stream = st;
+        h->has_last = true;
+    }
     h->launches++;
     return RSCM_B200_OK;
+}
+
+// ---- NCCL, loaded at run time (the library links against nothing but the CUDA runtime) -----------------------------------
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+constexpr int NCCL_INT8 = 0, NCCL_FLOAT64 = 8;
+
+NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    // 1. an explicit path; 2. the copy already mapped into this process (a Python host has torch's); 3. the system's
+    const char *env = getenv("RSCM_B200_NCCL_LIB");
+    void *lib = env ? dlopen(env, RTLD_NOW | RTLD_GLOBAL) : nullptr;
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return nullptr; }
+#define RSCM_SYM(field, name)                                                                   \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(lib, name));                         \
+    if (!api.field) { api.err = std::string("libnccl lacks ") + name; return nullptr; }
+    RSCM_SYM(GetUniqueId, "ncclGetUniqueId")
+    RSCM_SYM(CommInitRank, "ncclCommInitRank")
+    RSCM_SYM(CommDestroy, "ncclCommDestroy")
+    RSCM_SYM(AllGather, "ncclAllGather")
+    RSCM_SYM(Broadcast, "ncclBroadcast")
+    RSCM_SYM(GroupStart, "ncclGroupStart")
+    RSCM_SYM(GroupEnd, "ncclGroupEnd")
+    RSCM_SYM(GetErrorString, "ncclGetErrorString")
+#undef RSCM_SYM
+    api.lib = lib;
+    return &api;
 }
 
 template <class T> int ensure(rscm_b200_ensemble *h, T **p, int64_t *cap, int64_t need)
@@ -840,7 +940,7 @@ int rscm_b200_stretch_propose(const double *d_positions, int64_t ld, int n_cols,
     if (!(a > 1.0)) return fail(nullptr, RSCM_B200_EINVAL, "stretch parameter must be > 1"); // moves.rs:36-40
     const unsigned blocks = static_cast<unsigned>((n_active + 255) / 256);
     rscm_dev::stretch_propose_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_positions, ld, n_cols, active_begin, n_active, comp_begin, n_comp, a, seed, step, d_proposals, ld_proposals, d_z);
+        d_positions, ld, n_cols, active_begin, n_active, comp_begin, n_comp, a, seed, step, d_proposals, ld_proposals, d_z, nullptr);
     CU(cudaGetLastError());
     return RSCM_B200_OK;
 }
@@ -856,7 +956,7 @@ int rscm_b200_stretch_accept(double *d_positions, int64_t ld, int n_cols, int64_
     const unsigned blocks = static_cast<unsigned>((n_active + 255) / 256);
     rscm_dev::stretch_accept_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         d_positions, ld, n_cols, active_begin, n_active, d_proposals, ld_proposals, d_z, d_logpost_new, d_logpost, seed, step,
-        d_n_accepted);
+        d_n_accepted, nullptr);
     CU(cudaGetLastError());
     return RSCM_B200_OK;
 }
@@ -886,6 +986,412 @@ int rscm_b200_member_quantiles(const double *d_out, int64_t rows, int64_t S, int
     CU(cudaFuncSetAttribute(rscm_dev::member_quantiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     rscm_dev::member_quantiles_kernel<<<static_cast<unsigned>(rows * S), rscm_dev::Q_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
     CU(cudaGetLastError());
+    return RSCM_B200_OK;
+}
+
+// =====================================================================================================================
+// Multi-GPU: member sharding + the all-gather of per-member log-posteriors
+// =====================================================================================================================
+namespace {
+
+int cfail(rscm_b200_comm *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg;
+    g_global_err = msg;
+    return code;
+}
+
+#define CUC(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return cfail(c, RSCM_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+#define NCC(call)                                                                                        \
+    do {                                                                                                 \
+        int r_ = (call);                                                                                 \
+        if (r_ != 0) return cfail(c, RSCM_B200_ECOMM, std::string(#call) + ": " + nccl_api()->GetErrorString(r_)); \
+    } while (0)
+
+void shard_of(int64_t M, int rank, int world, int64_t *lo, int64_t *hi)
+{
+    *lo = (static_cast<int64_t>(rank) * M) / world;
+    *hi = (static_cast<int64_t>(rank + 1) * M) / world;
+}
+
+// map `bytes` of fresh device memory into every peer: cudaMalloc + cudaIpcGetMemHandle, handles exchanged with NCCL
+int symmetric_alloc(rscm_b200_comm *c, size_t bytes, rscm_b200_comm::Segment *out)
+{
+    NcclApi *nc = nccl_api();
+    rscm_b200_comm::Segment seg;
+    seg.bytes = bytes;
+    CUC(cudaMalloc(&seg.local, bytes));
+    CUC(cudaMemset(seg.local, 0, bytes));
+    seg.peer[c->rank] = seg.local;
+    if (c->world > 1 && c->p2p) {
+        cudaIpcMemHandle_t mine;
+        bool ok = cudaIpcGetMemHandle(&mine, seg.local) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        // exchange (handle, ok) of every rank
+        const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+        std::vector<char> host(rec * c->world, 0);
+        std::memcpy(host.data() + rec * c->rank, &mine, sizeof mine);
+        host[rec * c->rank + sizeof mine] = ok ? 1 : 0;
+        char *d_x = nullptr;
+        CUC(cudaMalloc(&d_x, rec * c->world));
+        CUC(cudaMemcpy(d_x, host.data(), rec * c->world, cudaMemcpyHostToDevice));
+        NCC(nc->AllGather(d_x + rec * c->rank, d_x, rec, NCCL_INT8, c->nccl, nullptr));
+        CUC(cudaStreamSynchronize(nullptr));
+        CUC(cudaMemcpy(host.data(), d_x, rec * c->world, cudaMemcpyDeviceToHost));
+        cudaFree(d_x);
+        bool all = true;
+        for (int p = 0; p < c->world; ++p) all = all && host[rec * p + sizeof mine];
+        for (int p = 0; p < c->world && all; ++p) {
+            if (p == c->rank) continue;
+            cudaIpcMemHandle_t hp;
+            std::memcpy(&hp, host.data() + rec * p, sizeof hp);
+            if (cudaIpcOpenMemHandle(&seg.peer[p], hp, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                all = false;
+            }
+        }
+        // every rank must take the same path: agree on the outcome
+        char *d_ok = nullptr;
+        CUC(cudaMalloc(&d_ok, c->world));
+        const char mine_ok = all ? 1 : 0;
+        CUC(cudaMemcpy(d_ok + c->rank, &mine_ok, 1, cudaMemcpyHostToDevice));
+        NCC(nc->AllGather(d_ok + c->rank, d_ok, 1, NCCL_INT8, c->nccl, nullptr));
+        CUC(cudaStreamSynchronize(nullptr));
+        std::vector<char> oks(c->world);
+        CUC(cudaMemcpy(oks.data(), d_ok, c->world, cudaMemcpyDeviceToHost));
+        cudaFree(d_ok);
+        for (char o : oks) all = all && o;
+        if (!all) {
+            for (int p = 0; p < c->world; ++p)
+                if (p != c->rank && seg.peer[p]) { cudaIpcCloseMemHandle(seg.peer[p]); seg.peer[p] = nullptr; }
+            cudaGetLastError();
+            c->p2p = false; // NCCL carries the all-gather instead
+        }
+    }
+    *out = seg;
+    return RSCM_B200_OK;
+}
+
+const rscm_b200_comm::Segment *segment_of(const rscm_b200_comm *c, const void *p, size_t bytes)
+{
+    for (size_t i = 1; i < c->segments.size(); ++i) {
+        const auto &sg = c->segments[i];
+        const char *b = static_cast<const char *>(sg.local), *q = static_cast<const char *>(p);
+        if (q >= b && q + bytes <= b + sg.bytes) return &sg;
+    }
+    return nullptr;
+}
+
+// all-gather of member blocks inside `buf` [S][M] (block of rank r = columns shard_of(r)), in place, over NCCL
+int allgather_in_place(rscm_b200_comm *c, double *buf, int64_t M, int64_t S, cudaStream_t st)
+{
+    NcclApi *nc = nccl_api();
+    if (c->world == 1) return RSCM_B200_OK;
+    if (S == 1 && M % c->world == 0) {
+        const int64_t n = M / c->world;
+        NCC(nc->AllGather(buf + n * c->rank, buf, static_cast<size_t>(n), NCCL_FLOAT64, c->nccl, st));
+        return RSCM_B200_OK;
+    }
+    // ragged blocks or several scenario rows: one broadcast per (row, owner) in a group
+    NCC(nc->GroupStart());
+    for (int64_t s = 0; s < S; ++s)
+        for (int r = 0; r < c->world; ++r) {
+            int64_t lo, hi;
+            shard_of(M, r, c->world, &lo, &hi);
+            if (hi > lo) {
+                int rc = nc->Broadcast(buf + s * M + lo, buf + s * M + lo, static_cast<size_t>(hi - lo), NCCL_FLOAT64, r, c->nccl, st);
+                if (rc != 0) { nc->GroupEnd(); return cfail(c, RSCM_B200_ECOMM, std::string("ncclBroadcast: ") + nc->GetErrorString(rc)); }
+            }
+        }
+    NCC(nc->GroupEnd());
+    return RSCM_B200_OK;
+}
+
+// one sharded log-posterior evaluation: kernel on this rank's member block + all-gather (fused over peer memory when the
+// destination is symmetric memory, NCCL otherwise)
+int logpost_sharded(rscm_b200_ensemble *h, rscm_b200_comm *c, const double *params, int64_t M, int layout, int64_t ld,
+                    const double *scen, int64_t S, double *lp_global, cudaStream_t st, bool pack)
+{
+    int64_t lo, hi;
+    shard_of(M, c->rank, c->world, &lo, &hi);
+    const int64_t Ml = hi - lo;
+    const int64_t S_eff = S > 0 ? S : 1;
+    LaunchOpts o;
+    o.lp_ld = M;
+    const double *p_local = params;
+    if (layout == 0) { o.ld_col = ld > 0 ? ld : M; p_local = params + lo; }
+    else p_local = params + lo * h->n_cols;
+    const rscm_b200_comm::Segment *sg = (c->world > 1 && c->p2p) ? segment_of(c, lp_global, static_cast<size_t>(S_eff * M) * 8) : nullptr;
+    if (sg) {
+        const size_t off = static_cast<const char *>(static_cast<const void *>(lp_global)) - static_cast<const char *>(sg->local);
+        o.n_peers = c->world;
+        for (int p = 0; p < c->world; ++p) {
+            o.peer_lp[p] = reinterpret_cast<double *>(static_cast<char *>(sg->peer[p]) + off) + lo;
+            o.peer_flag[p] = reinterpret_cast<unsigned long long *>(c->segments[0].peer[p]) + c->rank;
+        }
+        o.epoch = c->d_epoch;
+    }
+    if (Ml > 0) {
+        int rc = enqueue(h, p_local, Ml, layout, scen, S, nullptr, nullptr, lp_global + lo, nullptr, false, true, st, pack, &o);
+        if (rc != RSCM_B200_OK) { c->err = h->err; return rc; }
+    } else if (sg) {
+        return cfail(c, RSCM_B200_EINVAL, "fused all-gather needs at least one member per rank");
+    }
+    if (sg) {
+        rscm_dev::peer_wait_kernel<<<1, 32, 0, st>>>(c->flags, c->world, c->d_epoch, c->timeout_ns, c->d_error);
+        CUC(cudaGetLastError());
+        h->launches++;
+        return RSCM_B200_OK;
+    }
+    return allgather_in_place(c, lp_global, M, S_eff, st);
+}
+
+} // namespace
+
+int rscm_b200_comm_unique_id(void *unique_id)
+{
+    rscm_b200_comm *c = nullptr;
+    NcclApi *nc = nccl_api();
+    if (!nc) return cfail(nullptr, RSCM_B200_ECOMM, "NCCL is not available (set RSCM_B200_NCCL_LIB to libnccl.so.2)");
+    if (!unique_id) return cfail(nullptr, RSCM_B200_EINVAL, "null argument");
+    static_assert(RSCM_B200_UNIQUE_ID_BYTES == sizeof(NcclUniqueId), "unique id size");
+    NCC(nc->GetUniqueId(static_cast<NcclUniqueId *>(unique_id)));
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_comm_init(const void *unique_id, int rank, int world, int device, rscm_b200_comm **out)
+{
+    if (!out) return cfail(nullptr, RSCM_B200_EINVAL, "null argument");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return cfail(nullptr, RSCM_B200_EINVAL, "bad rank / world size");
+    if (world > rscm_dev::MAX_PEERS) return cfail(nullptr, RSCM_B200_EUNSUPPORTED, "at most 8 ranks (one NVSwitch domain) per communicator");
+    rscm_b200_comm *c = new rscm_b200_comm();
+    c->rank = rank;
+    c->world = world;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        delete c;
+        return cfail(nullptr, RSCM_B200_ENODEVICE, "no CUDA device available");
+    }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { delete c; return cfail(nullptr, RSCM_B200_ENODEVICE, "cannot select the requested CUDA device"); }
+    cudaGetDevice(&c->device);
+    if (world > 1) {
+        NcclApi *nc = nccl_api();
+        if (!nc || !unique_id) { delete c; return cfail(nullptr, RSCM_B200_ECOMM, "NCCL is not available or no unique id was given"); }
+        NcclUniqueId id;
+        std::memcpy(&id, unique_id, sizeof id);
+        const int r = nc->CommInitRank(&c->nccl, world, id, rank);
+        if (r != 0) { std::string m = std::string("ncclCommInitRank: ") + nc->GetErrorString(r); delete c; return cfail(nullptr, RSCM_B200_ECOMM, m); }
+        c->p2p = getenv("RSCM_B200_NO_P2P") == nullptr;
+    }
+    // control block: per-peer arrival flags, the epoch counter and the error word
+    rscm_b200_comm::Segment ctl;
+    int rc = symmetric_alloc(c, 256, &ctl);
+    if (rc != RSCM_B200_OK) { std::string m = c->err; rscm_b200_comm_destroy(c); return cfail(nullptr, rc, m); }
+    c->segments.push_back(ctl);
+    c->flags = static_cast<unsigned long long *>(ctl.local);
+    c->d_epoch = c->flags + rscm_dev::MAX_PEERS;
+    c->d_error = reinterpret_cast<int *>(c->flags + rscm_dev::MAX_PEERS + 1);
+    if (cudaMalloc(&c->d_iteration, sizeof(unsigned)) != cudaSuccess) { rscm_b200_comm_destroy(c); return cfail(nullptr, RSCM_B200_ECUDA, "device allocation failed"); }
+    cudaMemset(c->d_iteration, 0, sizeof(unsigned));
+    *out = c;
+    return RSCM_B200_OK;
+}
+
+void rscm_b200_comm_destroy(rscm_b200_comm *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (auto &sg : c->segments) {
+        for (int p = 0; p < c->world; ++p)
+            if (p != c->rank && sg.peer[p]) cudaIpcCloseMemHandle(sg.peer[p]);
+        cudaFree(sg.local);
+    }
+    cudaFree(c->d_iteration);
+    if (c->nccl && nccl_api()) nccl_api()->CommDestroy(c->nccl);
+    cudaGetLastError();
+    delete c;
+}
+
+const char *rscm_b200_comm_last_error(const rscm_b200_comm *c) { return c ? c->err.c_str() : g_global_err.c_str(); }
+int rscm_b200_comm_rank(const rscm_b200_comm *c) { return c ? c->rank : 0; }
+int rscm_b200_comm_world(const rscm_b200_comm *c) { return c ? c->world : 1; }
+int rscm_b200_comm_peer_access(const rscm_b200_comm *c) { return (c && c->world > 1 && c->p2p) ? 1 : 0; }
+
+int rscm_b200_comm_shard(const rscm_b200_comm *c, int64_t M, int64_t *begin, int64_t *end)
+{
+    if (!c || !begin || !end) return RSCM_B200_EINVAL;
+    shard_of(M, c->rank, c->world, begin, end);
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_comm_symmetric_alloc(rscm_b200_comm *c, size_t bytes, void **d_ptr)
+{
+    if (!c || !d_ptr || bytes == 0) return cfail(c, RSCM_B200_EINVAL, "null argument");
+    CUC(cudaSetDevice(c->device));
+    rscm_b200_comm::Segment sg;
+    int rc = symmetric_alloc(c, (bytes + 255) & ~size_t(255), &sg);
+    if (rc != RSCM_B200_OK) return rc;
+    c->segments.push_back(sg);
+    *d_ptr = sg.local;
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_allgather_f64(rscm_b200_comm *c, const double *d_local, int64_t n_local, double *d_global, void *stream)
+{
+    if (!c || !d_global || (n_local > 0 && !d_local) || n_local < 0) return cfail(c, RSCM_B200_EINVAL, "null argument");
+    CUC(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (c->world == 1) {
+        if (d_local != d_global) CUC(cudaMemcpyAsync(d_global, d_local, static_cast<size_t>(n_local) * 8, cudaMemcpyDeviceToDevice, st));
+        return RSCM_B200_OK;
+    }
+    NCC(nccl_api()->AllGather(d_local, d_global, static_cast<size_t>(n_local), NCCL_FLOAT64, c->nccl, st));
+    return RSCM_B200_OK;
+}
+
+int rscm_b200_logpost_sharded_device(rscm_b200_ensemble *h, rscm_b200_comm *c, const double *params, int64_t M, int params_layout,
+                                     const double *scenarios, int64_t S, double *logpost_global, void *stream)
+{
+    if (!h || !c || !logpost_global) return cfail(c, RSCM_B200_EINVAL, "null argument");
+    if (h->device < 0) return cfail(c, RSCM_B200_ENODEVICE, "host-only handle (device = -2) cannot run; there is no CPU fallback");
+    if (h->device != c->device) return cfail(c, RSCM_B200_EINVAL, "ensemble and communicator live on different devices");
+    if (M < 1) return cfail(c, RSCM_B200_EINVAL, "M must be positive");
+    CUC(cudaSetDevice(h->device));
+    return logpost_sharded(h, c, params, M, params_layout, 0, scenarios, S, logpost_global, static_cast<cudaStream_t>(stream), true);
+}
+
+int rscm_b200_comm_check(rscm_b200_comm *c)
+{
+    if (!c) return RSCM_B200_EINVAL;
+    int e = 0;
+    CUC(cudaMemcpy(&e, c->d_error, sizeof e, cudaMemcpyDeviceToHost));
+    if (e) return cfail(c, RSCM_B200_ECOMM, "a peer did not arrive at the fused all-gather within the timeout");
+    return RSCM_B200_OK;
+}
+
+// ---- the sampler loop behind the ABI: n iterations of (propose -> sharded log-posterior -> accept) x 2 halves, each
+// iteration replayed from one CUDA graph (sampler/ensemble.rs:412-546) -------------------------------------------------------
+int rscm_b200_sampler_iterate(rscm_b200_ensemble *h, rscm_b200_comm *c, const rscm_b200_sampler_state *s, const double *scenarios,
+                              int64_t S, int n_iterations, int use_graph, void *stream)
+{
+    if (!h || !c || !s) return cfail(c, RSCM_B200_EINVAL, "null argument");
+    if (h->device < 0) return cfail(c, RSCM_B200_ENODEVICE, "host-only handle (device = -2) cannot run; there is no CPU fallback");
+    if (!s->positions || !s->logpost || !s->proposals || !s->z || !s->logpost_new[0] || !s->logpost_new[1])
+        return cfail(c, RSCM_B200_EINVAL, "sampler state has null buffers");
+    const int64_t W = s->n_walkers, half = W / 2;
+    if (W < 2 || (W & 1)) return cfail(c, RSCM_B200_EINVAL, "the number of walkers must be even and at least 2"); // ensemble.rs:420-431
+    if (s->n_cols != h->n_cols) return cfail(c, RSCM_B200_EINVAL, "sampler state and parameter binding disagree on the column count");
+    if (!(s->a > 1.0)) return cfail(c, RSCM_B200_EINVAL, "stretch parameter must be > 1");
+    if (S > 1) return cfail(c, RSCM_B200_EINVAL, "the sampler evaluates one scenario per walker");
+    if (n_iterations < 1) return RSCM_B200_OK;
+    CUC(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned blocks = static_cast<unsigned>((half + 255) / 256);
+    const unsigned first = s->first_iteration;
+
+    // one iteration = two half-updates; `iter` is either the host's count (eager) or the device counter (graph)
+    auto one_iteration = [&](unsigned step_base, const unsigned *d_iter, bool pack) -> int {
+        for (int hidx = 0; hidx < 2; ++hidx) {
+            const int64_t a0 = hidx == 0 ? 0 : half, c0 = hidx == 0 ? half : 0;
+            const unsigned step = step_base + static_cast<unsigned>(hidx);
+            double *lpn = s->logpost_new[hidx];
+            rscm_dev::stretch_propose_kernel<<<blocks, 256, 0, st>>>(s->positions, s->ld, s->n_cols, a0, half, c0, half, s->a, s->seed, step,
+                                                                     s->proposals, half, s->z, d_iter);
+            CUC(cudaGetLastError());
+            int rc = logpost_sharded(h, c, s->proposals, half, 0, half, scenarios, S, lpn, st, pack && hidx == 0);
+            if (rc != RSCM_B200_OK) return rc;
+            rscm_dev::stretch_accept_kernel<<<blocks, 256, 0, st>>>(s->positions, s->ld, s->n_cols, a0, half, s->proposals, half, s->z, lpn,
+                                                                    s->logpost, s->seed, step, s->n_accepted, d_iter);
+            CUC(cudaGetLastError());
+            h->launches += 2;
+        }
+        return RSCM_B200_OK;
+    };
+
+    // Chain::push (sampler/chain.rs:63): every thin-th iteration's ensemble is kept, in device memory
+    auto record = [&](unsigned iteration) -> int {
+        if (!s->thin || !s->chain_positions || iteration % s->thin) return RSCM_B200_OK;
+        const int64_t k = iteration / s->thin;
+        if (k >= s->chain_capacity) return cfail(c, RSCM_B200_EINVAL, "chain buffers are too small for this iteration");
+        CUC(cudaMemcpy2DAsync(s->chain_positions + k * s->n_cols * W, static_cast<size_t>(W) * 8, s->positions, static_cast<size_t>(s->ld) * 8,
+                              static_cast<size_t>(W) * 8, static_cast<size_t>(s->n_cols), cudaMemcpyDeviceToDevice, st));
+        if (s->chain_logpost)
+            CUC(cudaMemcpyAsync(s->chain_logpost + k * W, s->logpost, static_cast<size_t>(W) * 8, cudaMemcpyDeviceToDevice, st));
+        return RSCM_B200_OK;
+    };
+
+    int done = 0;
+    // the first iteration of a call always runs eagerly: it packs the scenarios and sizes every buffer
+    {
+        int rc = one_iteration(2u * first, nullptr, true);
+        if (rc == RSCM_B200_OK) rc = record(first);
+        if (rc != RSCM_B200_OK) return rc;
+        done = 1;
+    }
+    if (!use_graph) {
+        for (; done < n_iterations; ++done) {
+            int rc = one_iteration(2u * (first + static_cast<unsigned>(done)), nullptr, false);
+            if (rc == RSCM_B200_OK) rc = record(first + static_cast<unsigned>(done));
+            if (rc != RSCM_B200_OK) return rc;
+        }
+        return RSCM_B200_OK;
+    }
+    if (done == n_iterations) return RSCM_B200_OK;
+    // graph: keyed by everything baked into the captured kernel arguments
+    std::vector<uintptr_t> key = {reinterpret_cast<uintptr_t>(h), reinterpret_cast<uintptr_t>(s->positions), reinterpret_cast<uintptr_t>(s->logpost),
+                                  reinterpret_cast<uintptr_t>(s->proposals), reinterpret_cast<uintptr_t>(s->z),
+                                  reinterpret_cast<uintptr_t>(s->logpost_new[0]), reinterpret_cast<uintptr_t>(s->logpost_new[1]),
+                                  reinterpret_cast<uintptr_t>(s->n_accepted), static_cast<uintptr_t>(s->ld), static_cast<uintptr_t>(W),
+                                  static_cast<uintptr_t>(s->seed), reinterpret_cast<uintptr_t>(scenarios), static_cast<uintptr_t>(S),
+                                  static_cast<uintptr_t>(h->n_obs_rows), static_cast<uintptr_t>(h->n_priors), reinterpret_cast<uintptr_t>(h->d_obs),
+                                  reinterpret_cast<uintptr_t>(h->d_priors), static_cast<uintptr_t>(std::hash<double>()(s->a))};
+    if (!c->graph_exec || key != c->graph_key) {
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        cudaStream_t cs;
+        CUC(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        cudaStream_t user = st;
+        st = cs;
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed);
+        int rc = RSCM_B200_OK;
+        if (e == cudaSuccess) {
+            const int64_t before = h->launches;
+            rc = one_iteration(0u, c->d_iteration, false);
+            if (rc == RSCM_B200_OK) {
+                rscm_dev::advance_iteration_kernel<<<1, 1, 0, cs>>>(c->d_iteration);
+                if (cudaGetLastError() != cudaSuccess) rc = RSCM_B200_ECUDA;
+            }
+            h->launches = before; // counted per replay below
+            e = cudaStreamEndCapture(cs, &graph);
+        }
+        st = user;
+        cudaStreamDestroy(cs);
+        if (rc != RSCM_B200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess || !graph) { cudaGetLastError(); return cfail(c, RSCM_B200_ECUDA, std::string("stream capture of the sampler iteration failed: ") + cudaGetErrorString(e)); }
+        e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { c->graph_exec = nullptr; return cfail(c, RSCM_B200_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+        c->graph_key = key;
+    }
+    const unsigned start = first + static_cast<unsigned>(done);
+    CUC(cudaMemcpyAsync(c->d_iteration, &start, sizeof start, cudaMemcpyHostToDevice, st)); // pageable source: copied before return
+    const bool fused = c->world > 1 && c->p2p && segment_of(c, s->logpost_new[0], static_cast<size_t>(half) * 8);
+    const int per_iter = 2 * (3 + (fused ? 1 : 0)) + 1; // propose, log-posterior, (peer wait), accept per half + the counter
+    for (; done < n_iterations; ++done) {
+        CUC(cudaGraphLaunch(c->graph_exec, st));
+        h->launches += per_iter;
+        int rc = record(first + static_cast<unsigned>(done));
+        if (rc != RSCM_B200_OK) return rc;
+    }
     return RSCM_B200_OK;
 }
 

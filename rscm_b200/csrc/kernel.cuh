@@ -27,6 +27,7 @@ namespace rscm_dev {
 constexpr int MAX_SLOTS = 224;  // component parameter slots per program
 constexpr int MAX_CELLS = 160;  // scalar storage cells (variables x regions); HalocarbonChemistry alone brings 86
 constexpr int MAX_OBS_ROWS = 4; // dense observation tables (one per observed variable)
+constexpr int MAX_PEERS = 8;    // GPUs of one NVSwitch domain that share a log-posterior buffer
 
 struct PriorDev {
     int kind;
@@ -78,6 +79,15 @@ struct KArgs {
     SummaryDev *summary;
     unsigned int *ticket;
     int t_start, t_stop, t_step; // selected time indices: t_start + k*t_step < t_stop
+    // log-posterior placement: run (s, m) goes to logpost[s * lp_ld + m]  (lp_ld = M unless this launch evaluates a member
+    // block of a larger ensemble in place: rscm_b200_logpost_sharded_device)
+    long long lp_ld;
+    // fused all-gather over peer memory: the same element is also stored into every peer's copy of the buffer
+    // (peer_lp[p] already offset like `logpost`), and the last CTA raises this rank's flag in every peer's flag array
+    int n_peers;
+    double *peer_lp[MAX_PEERS];
+    unsigned long long *peer_flag[MAX_PEERS]; // &flags_of_peer_p[this rank]
+    const unsigned long long *epoch;          // device counter: the flag value to raise is *epoch + 1
     // slot tables (compile-time indexed after unrolling -> constant-bank loads)
     int slot_col[MAX_SLOTS];
     double slot_def[MAX_SLOTS];
@@ -350,8 +360,18 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
             if (j < a.n_obs_rows) total += ll[j];
         double post = lp + total;
         if (bad || !(fabs(lp) <= 1.7976931348623157e308)) post = -RSCM_INF;
-        if (active) a.logpost[run] = post;
+        const long long lp_idx = static_cast<long long>(blockIdx.y) * a.lp_ld + m;
+        if (active) {
+            a.logpost[lp_idx] = post;
+            // fused all-gather: 8 B per run straight into every peer's buffer over NVLink (a warp's stores of one peer
+            // are one contiguous 256 B segment)
+            for (int p = 0; p < a.n_peers; ++p)
+                if (a.peer_lp[p] != a.logpost) a.peer_lp[p][lp_idx] = post;
+        }
 
+        __shared__ BlockPartial s_part[BLOCK / 32];
+        __shared__ bool s_last;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (a.summary) {
             // warp-shuffle + block reduction of the ensemble summary
             const bool fin = active && (fabs(post) <= 1.7976931348623157e308);
@@ -367,51 +387,16 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
                 vsum += __shfl_down_sync(0xffffffffu, vsum, off);
                 cnt += __shfl_down_sync(0xffffffffu, cnt, off);
             }
-            __shared__ BlockPartial s_part[BLOCK / 32];
-            __shared__ bool s_last;
-            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             if (lane == 0) s_part[warp] = BlockPartial{vmax, amax, vsum, cnt};
+        }
+        if (a.summary || a.n_peers > 0) {
+            // every thread's (remote) stores are ordered before this block's ticket
+            if (a.n_peers > 0) __threadfence_system();
             __syncthreads();
             const unsigned nblocks = gridDim.x * gridDim.y;
             const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
             if (threadIdx.x == 0) {
-                BlockPartial r = s_part[0];
-                for (int w = 1; w < BLOCK / 32; ++w) {
-                    const BlockPartial o = s_part[w];
-                    if (o.max_lp > r.max_lp || (o.max_lp == r.max_lp && o.argmax >= 0 && (r.argmax < 0 || o.argmax < r.argmax))) {
-                        r.max_lp = o.max_lp; r.argmax = o.argmax;
-                    }
-                    r.sum_finite += o.sum_finite;
-                    r.n_finite += o.n_finite;
-                }
-                a.partials[bid] = r;
-                __threadfence();
-                const unsigned t = atomicAdd(a.ticket, 1u);
-                s_last = (t == nblocks - 1);
-            }
-            __syncthreads();
-            if (s_last) {
-                // last block: deterministic tree over the per-block partials
-                __threadfence();
-                double bmax = -RSCM_INF, bsum = 0.0;
-                long long barg = -1, bcnt = 0;
-                for (unsigned i = threadIdx.x; i < nblocks; i += BLOCK) {
-                    const BlockPartial o = a.partials[i];
-                    if (o.max_lp > bmax || (o.max_lp == bmax && o.argmax >= 0 && (barg < 0 || o.argmax < barg))) { bmax = o.max_lp; barg = o.argmax; }
-                    bsum += o.sum_finite;
-                    bcnt += o.n_finite;
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double omax = __shfl_down_sync(0xffffffffu, bmax, off);
-                    const long long oarg = __shfl_down_sync(0xffffffffu, barg, off);
-                    if (omax > bmax || (omax == bmax && oarg >= 0 && (barg < 0 || oarg < barg))) { bmax = omax; barg = oarg; }
-                    bsum += __shfl_down_sync(0xffffffffu, bsum, off);
-                    bcnt += __shfl_down_sync(0xffffffffu, bcnt, off);
-                }
-                if (lane == 0) s_part[warp] = BlockPartial{bmax, barg, bsum, bcnt};
-                __syncthreads();
-                if (threadIdx.x == 0) {
+                if (a.summary) {
                     BlockPartial r = s_part[0];
                     for (int w = 1; w < BLOCK / 32; ++w) {
                         const BlockPartial o = s_part[w];
@@ -421,16 +406,87 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
                         r.sum_finite += o.sum_finite;
                         r.n_finite += o.n_finite;
                     }
-                    a.summary->max_logpost = r.max_lp;
-                    a.summary->argmax = r.argmax;
-                    a.summary->sum_finite = r.sum_finite;
-                    a.summary->n_finite = r.n_finite;
-                    a.summary->n_runs = a.runs;
-                    *a.ticket = 0u; // re-arm for the next launch
+                    a.partials[bid] = r;
                 }
+                __threadfence();
+                const unsigned t = atomicAdd(a.ticket, 1u);
+                s_last = (t == nblocks - 1);
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                if (a.summary) {
+                    // last block: deterministic tree over the per-block partials
+                    double bmax = -RSCM_INF, bsum = 0.0;
+                    long long barg = -1, bcnt = 0;
+                    for (unsigned i = threadIdx.x; i < nblocks; i += BLOCK) {
+                        const BlockPartial o = a.partials[i];
+                        if (o.max_lp > bmax || (o.max_lp == bmax && o.argmax >= 0 && (barg < 0 || o.argmax < barg))) { bmax = o.max_lp; barg = o.argmax; }
+                        bsum += o.sum_finite;
+                        bcnt += o.n_finite;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const double omax = __shfl_down_sync(0xffffffffu, bmax, off);
+                        const long long oarg = __shfl_down_sync(0xffffffffu, barg, off);
+                        if (omax > bmax || (omax == bmax && oarg >= 0 && (barg < 0 || oarg < barg))) { bmax = omax; barg = oarg; }
+                        bsum += __shfl_down_sync(0xffffffffu, bsum, off);
+                        bcnt += __shfl_down_sync(0xffffffffu, bcnt, off);
+                    }
+                    __syncthreads(); // s_part is reused
+                    if (lane == 0) s_part[warp] = BlockPartial{bmax, barg, bsum, bcnt};
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        BlockPartial r = s_part[0];
+                        for (int w = 1; w < BLOCK / 32; ++w) {
+                            const BlockPartial o = s_part[w];
+                            if (o.max_lp > r.max_lp || (o.max_lp == r.max_lp && o.argmax >= 0 && (r.argmax < 0 || o.argmax < r.argmax))) {
+                                r.max_lp = o.max_lp; r.argmax = o.argmax;
+                            }
+                            r.sum_finite += o.sum_finite;
+                            r.n_finite += o.n_finite;
+                        }
+                        a.summary->max_logpost = r.max_lp;
+                        a.summary->argmax = r.argmax;
+                        a.summary->sum_finite = r.sum_finite;
+                        a.summary->n_finite = r.n_finite;
+                        a.summary->n_runs = a.runs;
+                    }
+                }
+                if (a.n_peers > 0 && threadIdx.x < a.n_peers) {
+                    // every block of this rank has stored and fenced (its ticket came after a system-scope fence): tell
+                    // each peer that this rank's block of the buffer is complete for this epoch
+                    const unsigned long long e = *a.epoch + 1ull;
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flag[threadIdx.x]), "l"(e) : "memory");
+                }
+                if (threadIdx.x == 0) *a.ticket = 0u; // re-arm for the next launch
             }
         }
     }
+}
+
+// Completion of the fused all-gather: wait until every peer has raised its flag for epoch *epoch + 1, then advance the
+// epoch.  One warp; lane q watches peer q's flag (acquire at system scope).  A peer that never arrives (crashed process)
+// must not hang the GPU: after `timeout_ns` the kernel gives up and records the failure in *error.
+__global__ void peer_wait_kernel(const unsigned long long *flags, int n_peers, unsigned long long *epoch, unsigned long long timeout_ns,
+                                 int *error)
+{
+    const unsigned long long want = *epoch + 1ull;
+    if (threadIdx.x < n_peers) {
+        unsigned long long t0, t1, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v >= want) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) { atomicExch(error, 1); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+    if (threadIdx.x == 0) *epoch = want;
 }
 
 // scenario packing: user layout [S][var][T][R_v]  ->  staged rows [S][cell][Tpad]

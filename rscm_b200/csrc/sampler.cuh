@@ -48,8 +48,11 @@ enum { STRETCH_PROPOSE = 0, STRETCH_ACCEPT = 1 };
 // positions are SoA: element (column c, walker w) at pos[c * ld + w]
 __global__ void stretch_propose_kernel(const double *__restrict__ pos, long long ld, int n_cols, long long active0, long long n_active,
                                        long long comp0, long long n_comp, double a, unsigned long long seed, unsigned step,
-                                       double *__restrict__ prop, long long ld_prop, double *__restrict__ zs)
+                                       double *__restrict__ prop, long long ld_prop, double *__restrict__ zs,
+                                       const unsigned *__restrict__ iteration)
 {
+    // `iteration` (device counter, may be null) makes the launch replayable from a CUDA graph: step += 2 * *iteration
+    if (iteration) step += 2u * *iteration;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_active) return;
     const long long w = active0 + i;
@@ -70,8 +73,9 @@ __global__ void stretch_propose_kernel(const double *__restrict__ pos, long long
 __global__ void stretch_accept_kernel(double *__restrict__ pos, long long ld, int n_cols, long long active0, long long n_active,
                                       const double *__restrict__ prop, long long ld_prop, const double *__restrict__ zs,
                                       const double *__restrict__ lp_new, double *__restrict__ logp, unsigned long long seed, unsigned step,
-                                      unsigned long long *__restrict__ n_accepted)
+                                      unsigned long long *__restrict__ n_accepted, const unsigned *__restrict__ iteration)
 {
+    if (iteration) step += 2u * *iteration;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     bool acc = false;
     if (i < n_active) {
@@ -95,5 +99,8 @@ __global__ void stretch_accept_kernel(double *__restrict__ pos, long long ld, in
         if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_accepted, static_cast<unsigned long long>(__popc(ballot)));
     }
 }
+
+// end of a sampler iteration inside a captured graph: advance the device-side iteration counter
+__global__ void advance_iteration_kernel(unsigned *iteration) { *iteration += 1u; }
 
 } // namespace rscm_dev

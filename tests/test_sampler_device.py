@@ -144,3 +144,36 @@ def test_thinning_progress_and_argument_errors():
     t = torch.zeros(4, dtype=torch.float64, device="cuda")
     with pytest.raises(_ffi.EngineError, match="stretch parameter"):
         _ffi.check(_ffi.lib.rscm_b200_stretch_propose(t.data_ptr(), 2, 1, 0, 1, 1, 1, 1.0, 1, 0, t.data_ptr(), 1, t.data_ptr(), None))
+
+
+@pytest.mark.gpu
+def test_graph_replay_equals_eager_iterations_and_single_rank_comm_entry_points():
+    """rscm_b200_sampler_iterate: the iterations replayed from the captured CUDA graph (device-side iteration counter) give
+    the chain the eagerly enqueued iterations give, bit for bit; with one rank the sharded entry points reduce to the plain
+    ones (no NCCL needed)."""
+    import torch
+
+    from rscm_b200.dist import Comm
+
+    params, runner, target = two_layer_problem()
+    s = DeviceEnsembleSampler(params, runner, GaussianLikelihood(), target, seed=9)
+    init = WalkerInit.explicit(params.sample_random(96, np.random.default_rng(8)))
+    g = s.run(9, init, n_walkers=96, seed=1234, thin=2, use_graph=True)
+    e = s.run(9, init, n_walkers=96, seed=1234, thin=2, use_graph=False)
+    assert len(g) == len(e) == 5
+    for a, b in zip(g._samples, e._samples):
+        assert np.array_equal(a, b)
+    assert np.array_equal(np.asarray(g._log_probs), np.asarray(e._log_probs))
+    comm = Comm.single()
+    assert comm.world == 1 and not comm.peer_access and comm.shard(10) == (0, 10)
+    x = torch.arange(5, dtype=torch.float64, device="cuda")
+    y = torch.empty(5, dtype=torch.float64, device="cuda")
+    comm.allgather(x, y)
+    ens = runner.ensemble
+    p = torch.from_numpy(np.ascontiguousarray(init.positions.T)).cuda()
+    sc = torch.from_numpy(runner._scenarios).cuda()
+    lp = comm.symmetric_empty(96)
+    comm.log_posterior_sharded(ens, p, sc, lp, M=96, S=1, layout=0)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), np.arange(5.0))
+    assert np.array_equal(lp.cpu().numpy(), s.log_posterior_batch(init.positions))
