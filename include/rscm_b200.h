@@ -193,7 +193,8 @@ int rscm_b200_exogenous_variable(const rscm_b200_ensemble *h, int i);
 int rscm_b200_n_nodes(const rscm_b200_ensemble *h);
 int rscm_b200_execution_order(const rscm_b200_ensemble *h, int *order, int capacity);
 int rscm_b200_variable_source(const rscm_b200_ensemble *h, int component, const char *variable);
-/* canonical text of the fused device program chosen for this graph */
+/* canonical text of the fused device program chosen for this graph; for a run-time compiled program this includes the
+ * specialisation on the current parameter binding (unbound slots are literals), valid until the next call */
 const char *rscm_b200_program_signature(const rscm_b200_ensemble *h);
 /* 0: the program comes from the ahead-of-time registry; 1: compiled at run time (NVRTC, sm_100a) */
 int rscm_b200_program_is_jit(const rscm_b200_ensemble *h);

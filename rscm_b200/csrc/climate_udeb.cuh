@@ -6,18 +6,31 @@
 // heat uptake / ocean heat content :262-306), climate/lamcalc.rs (:85-290), climate/state.rs,
 // rscm-core/src/utils/linear_algebra.rs (thomas_solve :41-79, invert_4x4 :102-166).
 //
-// One thread = one member.  Where the state lives:
-//   * S[20]      (registers): LAMCALC result at the member's base ECS, upwelling rates, land / ground
-//                temperatures, alpha_eff, inter-hemispheric exchange, history length;
-//   * cx.sm      (shared memory, [50][2][BLOCK] per CTA, conflict-free): the two 50-layer ocean columns — the
-//                tridiagonal rows are built on the fly, d' overwrites T (fp32: also the c' columns);
-//   * cx.scratch (global, member-interleaved [100 + T][runs]): the c' columns of the Thomas sweeps (fp64), then
-//                the T*dt history of the cumulative-temperature feedback, summed newest-to-oldest in the
-//                reference's order;
-//   * cx.ctab    (shared memory, per graph): area factors af_top/af_bottom/af_diff, the entrainment
-//                combinations of the initial ocean profile of both hemispheres and the relative-depth factor
-//                of the diffusivity profile — they depend only on geometry parameters, which are
-//                per-graph (not bindable per member), so the host computes them once (graph.cpp).
+// FOUR LANES = ONE MEMBER (Prog::LANES = 4).  The reference solves, twelve times a year and for each hemisphere, a
+// 50-row tridiagonal system top to bottom: one 50-long recurrence with a division in the loop-carried chain.  Here the
+// system is eliminated from both ends towards the middle (rows 0..k the usual way, rows n-1..k+1 mirrored, a 2x2 solve
+// where they meet, substitution outwards — same solution up to rounding: the matrix is strictly diagonally dominant),
+// and each of the four half-sweeps of a member (2 hemispheres x 2 ends) belongs to one lane of a lane quad:
+//     lane & 1 = hemisphere (0 NH, 1 SH),   lane & 2 = end (0: top sweep, rows 0..k;  2: bottom sweep, rows n-1..k+1).
+// A lane keeps ITS <= 25 rows in registers for the whole run (the temperatures persist in S[], the eliminated
+// super-diagonal lives only inside a sub-step): there is no shared-memory column, no global scratch for the sweep and no
+// address arithmetic; the two ends of a hemisphere exchange three values per sub-step with __shfl_xor (edge temperatures
+// before the sweep, the pivot pair where the sweeps meet) and the quad shares the two sea-surface temperatures after it.
+// Everything that is not a row (LAMCALC, forcing, land / ground boxes, upwelling) is computed redundantly by the four
+// lanes — a few hundred instructions against 25 rows x 12 sub-steps — so all lanes hold identical scalar state.
+// Row coefficients that depend only on geometry (area factors, entrainment combinations of the initial profile,
+// relative depth of the diffusivity profile) come from a host-computed table laid out per lane role and row
+// (graph.cpp udeb_const_table), read with 128-bit shared-memory loads at immediate offsets.
+//
+// Where the state lives:
+//   * S[0..18]   (registers, identical in the four lanes): LAMCALC result at the member's base ECS, upwelling rates,
+//                land / ground temperatures, alpha_eff, inter-hemispheric exchange, history length;
+//   * S[19..43]  (registers): this lane's rows of the ocean column, sweep order (row 0 = the lane's end of the column);
+//   * cx.sm      (shared memory, [25][BLOCK] per CTA, conflict-free): the eliminated off-diagonal of the lane's rows,
+//                written by the sweep and read back by the substitution of the same sub-step;
+//   * cx.scratch (global, member-interleaved [T][runs]): the T*dt history of the cumulative-temperature feedback, each
+//                lane sums a quarter of the window newest-to-oldest and the quad adds the four partial sums;
+//   * cx.ctab    (shared memory, per graph): the role tables.
 #pragma once
 
 namespace rscm_dev {
@@ -28,11 +41,13 @@ enum {
     U_LHC_ON, U_KLG, U_LHC_THICK, U_RFR0, U_RFR1, U_RFR2, U_RFR3, U_EFF_APPLY, U_EFF_CO2, U_PROFILE, U_STEPS, U_TMAX, U_NPARAM
 };
 enum { US_OK, US_LAMO, US_LAML, US_EFF, US_QF0, US_QF1, US_QF2, US_QF3, US_W0, US_W1, US_LAND0, US_LAND1, US_GR0, US_GR1,
-       US_AE0, US_AE1, US_HX0, US_HX1, US_NHIST, US_N };
+       US_AE0, US_AE1, US_HX0, US_HX1, US_NHIST, US_T };
 
-constexpr int UDEB_MAXL = 50;
-constexpr int UDEB_ROW = 2 * BLOCK; // per-thread shared-memory scratch: values per layer and CTA {T_nh, T_sh}
-constexpr int UDEB_CT = 8;          // constant table: values per layer
+#define RSCM_INF_F (__int_as_float(0x7f800000))
+constexpr int UDEB_LANES = 4;
+constexpr int UDEB_MAXR = 25;       // rows per lane (n_layers <= 50)
+constexpr int UDEB_CT = 6;          // role table: doubles per row {near area, far area, af_diff, g, omr, af_top}
+constexpr int UDEB_NS = US_T + UDEB_MAXR;
 
 // f64::min / f64::max: NaN-ignoring, like fmin / fmax
 __device__ __forceinline__ double r_min(double a, double b) { return fmin(a, b); }
@@ -41,17 +56,16 @@ __device__ __forceinline__ double r_max(double a, double b) { return fmax(a, b);
 __device__ __forceinline__ float r_max(float a, float b) { return fmaxf(a, b); }
 
 // Reciprocal for the Thomas sweep: the pivots of the diagonally dominant ocean-column system are >= 1, never
-// subnormal or infinite, so the special-case slow path of 1/x (a divergent call that also keeps the compiler from
-// interleaving the two hemispheres' recurrences) is dropped: MUFU seed (~2^-20) + two Newton steps (<= 1 ulp; a NaN
-// pivot stays NaN).
+// subnormal or infinite, so the special-case slow path of 1/x is dropped: MUFU seed (relative error e0 ~ 2^-20) and
+// one cubically convergent step r (1 + e + e^2), e = 1 - x r: error e0^3 ~ 2^-60 plus rounding (<= 1 ulp; a NaN pivot
+// stays NaN).  Three dependent FMAs in the loop-carried chain of the sweep instead of four.
 __device__ __forceinline__ double r_rcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 __device__ __forceinline__ float r_rcp(float x) { return __frcp_rn(x); }
 
@@ -148,6 +162,24 @@ template <class R> __device__ __forceinline__ R udeb_sst_to_air(const R *P, R ss
     return alpha * sst + gamma * sst * sst;
 }
 
+// sst_to_air_temperature with the member's constants hoisted: t_star = -(alpha - 1)/(2 gamma) and the offset of the
+// linear continuation above it (mod.rs:377-397) do not change during a run
+template <class R> struct UdebAir { R alpha, gamma, t_star, offs; bool quad; };
+template <class R> __device__ __forceinline__ UdebAir<R> udeb_air_constants(const R *P)
+{
+    UdebAir<R> a;
+    a.alpha = P[U_TA_ALPHA]; a.gamma = P[U_TA_GAMMA];
+    a.quad = r_abs(a.gamma) > R(1e-15);
+    a.t_star = a.quad ? -(a.alpha - R(1)) / (R(2) * a.gamma) : R(0);
+    a.offs = a.alpha * a.t_star + a.gamma * a.t_star * a.t_star - a.t_star;
+    return a;
+}
+template <class R> __device__ __forceinline__ R udeb_sst_to_air(const UdebAir<R> &a, R sst)
+{
+    const R lin = sst + a.offs, par = a.alpha * sst + a.gamma * sst * sst;
+    return (a.quad && !(sst < a.t_star)) ? lin : par;
+}
+
 template <class R> __device__ __forceinline__ R udeb_land_temperature(const R *P, R ocean_temp, R land_forcing, R f_l, R lambda_land)
 {
     const R num = land_forcing * f_l + P[U_KLO] * P[U_AMP] * ocean_temp;
@@ -170,9 +202,8 @@ constexpr int CLIMATE_UDEB_ND = 1;
 template <class R> __device__ __forceinline__ void climate_udeb_prepare(const R *, R *D) { D[0] = R(0); }
 
 // from_parameters + create_initial_state
-template <class R> __device__ inline void climate_udeb_init_state(const R *P, const R *, R *S, const StepCtx<R> &cx, NodeRef nr)
+template <class R, int N> __device__ inline void climate_udeb_init_state(const R *P, const R *, R *S, const StepCtx<R> &, NodeRef)
 {
-    const int n = static_cast<int>(P[U_NLAYERS]);
     R area[4], q[4];
     udeb_fractions(P, area);
     udeb_qfrac(P, area, q);
@@ -186,190 +217,167 @@ template <class R> __device__ inline void climate_udeb_init_state(const R *P, co
     S[US_AE0] = S[US_AE1] = P[U_TA_ALPHA];
     S[US_HX0] = S[US_HX1] = R(0);
     S[US_NHIST] = R(0);
-    R *col = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R)));
-    for (int i = 0; i < n; ++i) col[i * UDEB_ROW] = col[i * UDEB_ROW + BLOCK] = R(0);
+#pragma unroll
+    for (int j = 0; j < UDEB_MAXR; ++j) S[US_T + j] = R(0);
 }
 
-// Constants of one model year for step_hemisphere (everything that does not change between sub-steps).
+// Constants of one model year for the sweeps (everything that does not change between sub-steps), for this lane's
+// hemisphere.
 template <class R> struct UdebYear {
-    R cA, cA1, cM, dt_mix, dtdz, dt_cmix, kc, kmin, dkdt_c, pi_ratio, tmax;
-    R tfb_dt[2], famp[2], lhc_c[2]; // per hemisphere
+    R cA, cM, dt_mix, dtdz, dt_cmix, kc, kmin, dkdt_c, pi_ratio, tmax;
+    R kcA, kminA; // kc cA, kmin cA: interior rows compute k cA = max(omr (dkdt_c dT cA) + kc cA, kmin cA) directly
+    R tfb_dt, famp, lhc_c;
     bool lhc;
 };
 
-// step_hemisphere for both hemispheres at once, each solved by two-ended elimination.
-//
-// The reference runs thomas_solve top to bottom (linear_algebra.rs:41-79): one 50-long recurrence with a
-// reciprocal in the loop-carried chain, i.e. pure latency for a thread.  The same tridiagonal system is solved here
-// by eliminating from both ends towards the middle ("burn at both ends"): rows 0..k the usual way
-// (x_i = d'_i - c'_i x_{i+1}), rows n-1..k+1 mirrored (x_i = d"_i - a'_i x_{i-1}), a 2x2 solve where they meet,
-// and substitution outwards in both directions.  Same solution up to rounding (the system is strictly diagonally
-// dominant), but with the two hemispheres that makes four independent recurrences per thread instead of one.
-// Rows are built on the fly; -c' (or -a') goes to the per-thread c' column and d' over T; one reciprocal per row; the
-// temperature cap applies to what is stored, the substitution carries the uncapped value (ocean_column.rs:226-238).
-// col  = this thread's ocean columns, layer-major: layer i holds {T_nh, T_sh} at col[(2*i + h) * BLOCK];
-// cp   = this thread's c' columns, layer i at cp[(2*i + h) * cs] (where they live: see climate_udeb_solve).
-// ctab = per layer {af_top, af_bottom, af_diff, omr_i, g_nh, g_sh, omr_{i-1}, 0} (graph.cpp udeb_const_table).
-template <class R> struct UdebRow { R at, ab, ad, om, g[2], omu; };
+template <class R> struct UdebRow { R an, af, ad, g, om, at; };
 
 template <class R> __device__ __forceinline__ UdebRow<R> udeb_row(const double *ct)
 {
     const double2 c01 = *reinterpret_cast<const double2 *>(ct), c23 = *reinterpret_cast<const double2 *>(ct + 2),
-                  c45 = *reinterpret_cast<const double2 *>(ct + 4); // 64-byte rows: 16-byte aligned
+                  c45 = *reinterpret_cast<const double2 *>(ct + 4); // 48-byte rows: 16-byte aligned
     UdebRow<R> r;
-    r.at = R(c01.x); r.ab = R(c01.y); r.ad = R(c23.x); r.om = R(c23.y); r.g[0] = R(c45.x); r.g[1] = R(c45.y); r.omu = R(ct[6]);
+    r.an = R(c01.x); r.af = R(c01.y); r.ad = R(c23.x); r.g = R(c23.y); r.om = R(c45.x); r.at = R(c45.y);
     return r;
 }
 
-template <class R>
-__device__ __forceinline__ void udeb_step_both(const UdebYear<R> &y, const R *P, R *S, const double *ctab, int n, R *col, R *cp,
-                                               long long cs, R forcing_nh, R forcing_sh)
+template <class R> __device__ __forceinline__ R udeb_shx(unsigned mask, R v, int x) { return __shfl_xor_sync(mask, v, x); }
+
+// f64::max(x, lo) / f64::min(x, hi) for a bound that is not NaN (the year set-up replaces a NaN bound by -inf / +inf,
+// which is what the NaN-ignoring f64::max / min make of it): one compare and a select instead of the library fmax / fmin
+// (compare, NaN quieting, selects: eight instructions).  A NaN x yields the bound, as f64::max / min do.
+template <class R> __device__ __forceinline__ R udeb_floor(R x, R lo) { return x > lo ? x : lo; }
+template <class R> __device__ __forceinline__ R udeb_cap(R x, R hi) { return x < hi ? x : hi; }
+
+// One sub-step of step_hemisphere for this lane's half-sweep.
+//
+// Row i of the system (ocean_column.rs:118-160), with tup = k_{i-1} dt/(dz dz_up), tdn = k_i dt/dz^2, tul = w dt/dz:
+//     -a_i = tup af_top_i,   -c_i = (tdn + tul) af_bottom_i,   b_i = 1 - a_i + tdn af_bottom_i + tul af_top_i,
+//     d_i = T_i + pi_ratio tul T_0 af_diff_i + dt/dz dw g_i.
+// A sweep meets the coupling towards the row it has already eliminated ("near") and the one towards the next row
+// ("far"); for the top sweep near = -a_i, far = -c_i, for the bottom sweep the other way round.  With the diffusivity the
+// previous row computed carried along, both are (carry + u_n) area_n and (k_new + u_f) area_f, where (u_n, u_f) =
+// (0, tul) / (tul, 0) and the areas come from the role table — one instruction stream for all four lanes, no selects:
+//     b_i = 1 + near + far + tul (af_top_i - af_bottom_i),        pivot = b_i - near f_prev,
+//     f_i = far / pivot,   d'_i = (d_i + near d'_prev) / pivot,   back substitution  x_i = d'_i + f_i x_next.
+// T holds the lane's rows (sweep order); on return it holds the new temperatures, capped (ocean_column.rs:226-238: the
+// cap applies to what is stored, the substitution carries the uncapped value).
+// N = n_layers is a compile-time constant of the program (the graph compiler passes it as a template argument), so the
+// row loops are straight-line code over register rows: the top sweep owns rows 0..K (NT = K + 1 of them), the bottom
+// sweep rows N-1..K+1 (NB = N - K - 1, one more than NT when N is odd — that row is the only predicated one).
+template <class R, int N>
+__device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, const R *S, const double *tab, bool bottom, int h,
+                                             unsigned mask, R *T, R *F, R forcing)
 {
-    const R forcing[2] = {forcing_nh, forcing_sh};
-    R dkc[2], tul[2], pt0[2], dwc[2];
-    R tu[2], cn[2], dpt[2]; // top sweep:    k_{i-1}/(dz dz_up) dt, -c'_{i-1}, d'_{i-1}
-    R tb[2], an[2], dpb[2]; // bottom sweep: k_i/(dz dz) dt,       -a'_{i+1}, d"_{i+1}
-    R *rb = col + (n - 1) * UDEB_ROW;
-    R *pb = cp + (n - 1) * 2 * cs, *pt = cp; // c' columns: layer i, hemisphere h at cp[(2*i + h) * cs]
-    const double *cb = ctab + (n - 1) * UDEB_CT;
+    constexpr int K = (N - 2) >> 1, NT = K + 1, NB = N - K - 1;
+    static_assert(NT >= 1 && NB >= NT && NB - NT <= 1 && NB <= UDEB_MAXR, "row split");
+    // F: the eliminated off-diagonal of this lane's rows, row j at F[j * BLOCK] (this thread's shared-memory column:
+    // consecutive threads, consecutive words); it lives only inside the sub-step
+    // edge temperatures of this hemisphere before the solve: the mixed layer (top lane's row 0) and the bottom layer
+    const R tedge = T[0];
+    const R tpart = udeb_shx(mask, tedge, 2);
+    const R t0 = bottom ? tpart : tedge, tbot = bottom ? tedge : tpart;
+    const R w = h ? S[US_W1] : S[US_W0];
+    const R dkc = y.dkdt_c * (t0 - tbot), dkcA = dkc * y.cA;
+    const R delta_w = w - P[U_W0];
+    const R dwv = (r_abs(delta_w) > R(1e-15)) ? delta_w : R(0);
+    const R dwc = y.dtdz * dwv;
+    const R tul = w * y.dtdz;
+    const R pt0 = y.pi_ratio * tul * t0;
+    const R u_n = bottom ? tul : R(0), u_f = bottom ? R(0) : tul;
+    // Division-free elimination.  With q_j = product of the pivots up to row j (q_{-1} = 1) the sweep
+    //     pivot_j = b_j - near_j f_{j-1},   f_j = far_j / pivot_j,   d'_j = (d_j + near_j d'_{j-1}) / pivot_j
+    // becomes three LINEAR recurrences
+    //     g_j = far_j q_{j-1},   q_j = b_j q_{j-1} - near_j g_{j-1},   D_j = d_j q_{j-1} + near_j D_{j-1},
+    // with f_j = g_j / q_j and d'_j = D_j / q_j.  The loop-carried dependence is one FMA per row (q) instead of an FMA, a
+    // reciprocal and a multiply; the 25 reciprocals no longer depend on each other, so a warp overlaps them.  Same
+    // numbers up to rounding; the pivots of this system lie between 1 and a few units, so q stays far inside the range.
+    R carry, q1, g1, D1, fp, dp;
     {
-        const R at0 = R(ctab[0]), ab0 = R(ctab[1]), om0 = R(ctab[3]);
-        const UdebRow<R> c = udeb_row<R>(cb);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const R w = S[US_W0 + h];
-            const R t0 = col[h * BLOCK]; // mixed-layer temperature before the solve (entrainment terms)
-            const R tbot = rb[h * BLOCK];
-            dkc[h] = y.dkdt_c * (t0 - tbot);
-            const R delta_w = w - P[U_W0];
-            const R dwv = (r_abs(delta_w) > R(1e-15)) ? delta_w : R(0);
-            dwc[h] = y.dtdz * dwv;
-            tul[h] = w * y.dtdz;
-            pt0[h] = y.pi_ratio * tul[h] * t0;
-            { // row 0: mixed layer
-                const R k0 = r_max(om0 * dkc[h] + y.kc, y.kmin);
-                const R term_diff = k0 * y.cM, term_upwell = w * y.dt_mix;
-                const R b0 = R(1) + y.tfb_dt[h] * at0 + term_diff * ab0 + term_upwell * y.pi_ratio * ab0;
-                R d0 = t0 + (forcing[h] * y.famp[h] + S[US_HX0 + h]) * y.dt_cmix * at0;
-                if (y.lhc) d0 -= y.lhc_c[h] * (S[US_LAND0 + h] - S[US_GR0 + h]) * at0;
-                d0 += y.dt_mix * dwv * R(ctab[4 + h]);
-                const R r = r_rcp(b0);
-                cn[h] = (term_diff + term_upwell) * ab0 * r;
-                dpt[h] = d0 * r;
-                pt[h * cs] = cn[h];
-                col[h * BLOCK] = dpt[h];
-                tu[h] = k0 * y.cA1; // the layer below the mixed layer sees half a layer thickness upwards
-            }
-            { // row n-1: bottom layer (no diffusion below)
-                const R ku = r_max(c.omu * dkc[h] + y.kc, y.kmin);
-                tb[h] = ku * y.cA;
-                const R m = tb[h] * c.at;
-                const R bi = R(1) + m + tul[h] * c.at;
-                const R di = tbot + pt0[h] * c.at + dwc[h] * c.g[h];
-                const R r = r_rcp(bi);
-                an[h] = m * r;
-                dpb[h] = di * r;
-                pb[h * cs] = an[h];
-                rb[h * BLOCK] = dpb[h];
-            }
-        }
+        const UdebRow<R> c = udeb_row<R>(tab);
+        const R k = udeb_floor(c.om * dkc + y.kc, y.kmin);
+        // row 0 of the top sweep: mixed layer (ocean_column.rs:93-150); of the bottom sweep: bottom layer, no diffusion
+        // below (:163-175).  Both are evaluated branch-free and selected (a few dozen instructions per sub-step).
+        const R term_diff = k * y.cM, term_upwell = w * y.dt_mix;
+        const R b_top = R(1) + y.tfb_dt * c.at + term_diff * c.af + term_upwell * y.pi_ratio * c.af;
+        R d_top = t0 + (forcing * y.famp + (h ? S[US_HX1] : S[US_HX0])) * y.dt_cmix * c.at;
+        if (y.lhc) d_top -= y.lhc_c * ((h ? S[US_LAND1] : S[US_LAND0]) - (h ? S[US_GR1] : S[US_GR0])) * c.at;
+        d_top += y.dt_mix * dwv * c.g;
+        const R m = k * y.cA * c.at;
+        const R b_bot = R(1) + m + tul * c.at;
+        const R d_bot = tbot + pt0 * c.at + dwc * c.g;
+        q1 = bottom ? b_bot : b_top;
+        g1 = bottom ? m : (term_diff + term_upwell) * c.af;
+        D1 = bottom ? d_bot : d_top;
+        const R r = r_rcp(q1);
+        fp = g1 * r;
+        dp = D1 * r;
+        carry = k * y.cA;
+        F[0] = fp;
+        T[0] = dp;
     }
-    // interior rows 1..n-2: the top sweep takes 1..k, the bottom sweep n-2..k+1 (one more when n is odd)
-    const int k = (n - 2) >> 1;
-    R *rt = col;
-    const double *ctp = ctab;
-    auto bottom_row = [&](R cu) {
-        rb -= UDEB_ROW; cb -= UDEB_CT; pb -= 2 * cs;
-        const UdebRow<R> c = udeb_row<R>(cb);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const R ku = r_max(c.omu * dkc[h] + y.kc, y.kmin);
-            const R m = ku * cu * c.at; // -a_i
-            const R tdd = tb[h];
-            const R bi = R(1) + m + tdd * c.ab + tul[h] * c.at;
-            const R cnum = (tdd + tul[h]) * c.ab; // -c_i
-            const R di = rb[h * BLOCK] + pt0[h] * c.ad + dwc[h] * c.g[h];
-            const R r = r_rcp(bi - cnum * an[h]);
-            an[h] = m * r;
-            dpb[h] = (di + cnum * dpb[h]) * r;
-            pb[h * cs] = an[h];
-            rb[h * BLOCK] = dpb[h];
-            tb[h] = ku * y.cA;
-        }
+    auto row = [&](int j) {
+        const UdebRow<R> c = udeb_row<R>(tab + j * UDEB_CT);
+        const R knew = udeb_floor(c.om * dkcA + y.kcA, y.kminA);
+        const R near = (carry + u_n) * c.an;
+        const R far = (knew + u_f) * c.af;
+        const R bi = (R(1) + near) + (far + tul * c.ad);
+        const R di = T[j] + pt0 * c.ad + dwc * c.g;
+        const R g = far * q1;
+        const R q = bi * q1 - near * g1;
+        const R D = di * q1 + near * D1;
+        const R r = r_rcp(q);
+        fp = g * r;
+        dp = D * r;
+        F[j * BLOCK] = fp;
+        T[j] = dp;
+        carry = knew;
+        q1 = q; g1 = g; D1 = D;
     };
-    for (int j = 0; j < k; ++j) {
-        rt += UDEB_ROW; ctp += UDEB_CT; pt += 2 * cs;
-        const UdebRow<R> c = udeb_row<R>(ctp);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const R tdd = r_max(c.om * dkc[h] + y.kc, y.kmin) * y.cA;
-            const R m = tu[h] * c.at; // -a_i
-            const R bi = R(1) + m + tdd * c.ab + tul[h] * c.at;
-            const R cnum = (tdd + tul[h]) * c.ab; // -c_i
-            const R di = rt[h * BLOCK] + pt0[h] * c.ad + dwc[h] * c.g[h];
-            const R r = r_rcp(bi - m * cn[h]);
-            cn[h] = cnum * r;
-            dpt[h] = (di + m * dpt[h]) * r;
-            pt[h * cs] = cn[h];
-            rt[h * BLOCK] = dpt[h];
-            tu[h] = tdd;
-        }
-        bottom_row(y.cA);
+    for (int j = 1; j < NT; ++j) row(j);
+    if (NB > NT) {
+        if (bottom) row(NB - 1);
     }
-    if (n & 1) bottom_row(n == 3 ? y.cA1 : y.cA);
-    // rt = row k (top sweep's last), rb = row k+1 (bottom sweep's last): 2x2 solve, then outwards
-    R xu[2], xd[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        xu[h] = (dpt[h] + cn[h] * dpb[h]) * r_rcp(R(1) - cn[h] * an[h]);
-        xd[h] = dpb[h] + an[h] * xu[h];
-        rt[h * BLOCK] = r_min(xu[h], y.tmax);
-        rb[h * BLOCK] = r_min(xd[h], y.tmax);
-    }
-    auto down_row = [&]() {
-        rb += UDEB_ROW; pb += 2 * cs;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            xd[h] = rb[h * BLOCK] + pb[h * cs] * xd[h];
-            rb[h * BLOCK] = r_min(xd[h], y.tmax);
+    // where the sweeps meet: x_K = d'_K + f_K x_{K+1} (top), x_{K+1} = d"_{K+1} + f"_{K+1} x_K (bottom)
+    const R fq = udeb_shx(mask, fp, 2), dq = udeb_shx(mask, dp, 2);
+    const R f_top = bottom ? fq : fp, d_top = bottom ? dq : dp, d_bot = bottom ? dp : dq;
+    const R x_top = (d_top + f_top * d_bot) * r_rcp(R(1) - fp * fq);
+    R x = bottom ? dp + fp * x_top : x_top;
+    if (NB > NT) {
+        if (bottom) {
+            T[NB - 1] = udeb_cap(x, y.tmax);
+            x = T[NT - 1] + F[(NT - 1) * BLOCK] * x;
         }
-    };
-    for (int j = 0; j < k; ++j) {
-        rt -= UDEB_ROW; pt -= 2 * cs;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            xu[h] = rt[h * BLOCK] + pt[h * cs] * xu[h];
-            rt[h * BLOCK] = r_min(xu[h], y.tmax);
-        }
-        down_row();
     }
-    if (n & 1) down_row();
+    T[NT - 1] = udeb_cap(x, y.tmax);
+#pragma unroll
+    for (int j = NT - 2; j >= 0; --j) {
+        x = T[j] + F[j * BLOCK] * x;
+        T[j] = udeb_cap(x, y.tmax);
+    }
 }
 
 // in: [ERF at_start, ERF at_end, Surface Temperature[4] at_start]
 // out: [Heat Uptake, Ocean Heat Content, Sea Surface Temperature, Surface Temperature[4]]
-template <class R>
+template <class R, int N>
 __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &cx, R *S, NodeRef nr)
 {
-    if (S[US_OK] == R(0)) return false; // from_parameters failed for this member (LAMCALC did not converge)
-    const int n = static_cast<int>(P[U_NLAYERS]), steps_n = static_cast<int>(P[U_STEPS]);
-    R *col = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R))); // layer-major {T_nh, T_sh}, see udeb_step_both
-    // The c' columns of the Thomas sweeps.  The per-thread shared-memory scratch is 100 8-byte words: in fp64 the
-    // ocean columns fill it (two CTAs per SM) and c' goes to this run's rows of the global scratch (coalesced, lives
-    // in L2: written and read back within one sub-step); in fp32 it holds both.
-    R *cp;
-    long long cs;
-    if (sizeof(R) == 8) {
-        cp = reinterpret_cast<R *>(cx.scratch0 + static_cast<long long>(nr.scr) * cx.runs) + cx.run;
-        cs = cx.runs;
-    } else {
-        cp = col + 2 * UDEB_MAXL * BLOCK;
-        cs = BLOCK;
-    }
-    const double *ctab = cx.ctab + nr.ctab;
+    // No early return: the four lanes of a member take every shuffle together, and the members of a warp must too.  A
+    // member whose from_parameters failed (LAMCALC did not converge) computes on and reports failure at the end.
+    const bool ok = S[US_OK] != R(0);
+    const int steps_n = static_cast<int>(P[U_STEPS]);
+    const int q = cx.role, h = q & 1;
+    const bool bottom = (q & 2) != 0;
+    const unsigned mask = cx.mask;
+    constexpr int K = (N - 2) >> 1, NT = K + 1, NB = N - K - 1;
+    R *T = S + US_T;
+    R *F = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R)));
+    const double *tab = cx.ctab + nr.ctab + q * (UDEB_MAXR * UDEB_CT);
     const R erf_start = in[0], erf_end = in[1];
-    if (col[0] == R(0) && in[2] != R(0)) { // warm start from non-zero initial surface temperatures
-        col[0] = in[2]; col[BLOCK] = in[4];
+    const int lane = static_cast<int>(threadIdx.x) & 31, quad = lane & ~3;
+    if (__shfl_sync(mask, T[0], quad) == R(0) && in[2] != R(0)) { // warm start from non-zero initial surface temperatures (mod.rs:439-448)
+        if (!bottom) T[0] = h ? in[4] : in[2];
         S[US_LAND0] = in[3]; S[US_LAND1] = in[5];
         S[US_GR0] = S[US_LAND0]; S[US_GR1] = S[US_LAND1];
     }
@@ -377,14 +385,13 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     const R steps = R(steps_n);
     const R dt_sub = dt_year / steps;
 
-    // adjusted_ecs: sum of T*dt over the last `period` years, newest to oldest
+    // adjusted_ecs: sum of T*dt over the last `period` years
     const int nhist = static_cast<int>(S[US_NHIST]);
     R cum_t = R(0);
     {
         // Which entries the window covers follows from the time axis alone (shared memory, block-uniform): entries
-        // [first, nhist) count fully, entry first-1 with weight `partial` if the window ends inside it.  The values are
-        // then summed in the reference's order with independent global loads the compiler can batch (a loop that decides
-        // and loads in one go serialises a load latency per year of history: a third of the kernel's time at 350 years).
+        // [first, nhist) count fully, entry first-1 with weight `partial` if the window ends inside it.  Each lane of
+        // the quad sums every fourth entry, newest first, with independent loads; the quad adds the partial sums.
         R rem = P[U_FB_PERIOD], partial = R(0);
         int first = nhist;
         for (int i = nhist - 1; i >= 0; --i) {
@@ -393,11 +400,13 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
             if (dt <= rem) { first = i; rem -= dt; }
             else { partial = rem / dt; rem = R(0); }
         }
-        const double *hist = cx.scratch + static_cast<long long>(nr.scr + 2 * UDEB_MAXL) * cx.runs;
+        const double *hist = cx.scratch + static_cast<long long>(nr.scr) * cx.runs;
         R sum = R(0);
-#pragma unroll 8
-        for (int i = nhist - 1; i >= first; --i) sum += R(hist[static_cast<long long>(i) * cx.runs]);
-        if (partial > R(0) && first > 0) sum += R(hist[static_cast<long long>(first - 1) * cx.runs]) * partial;
+#pragma unroll 4
+        for (int i = nhist - 1 - q; i >= first; i -= UDEB_LANES) sum += R(hist[static_cast<long long>(i) * cx.runs]);
+        if (q == 0 && partial > R(0) && first > 0) sum += R(hist[static_cast<long long>(first - 1) * cx.runs]) * partial;
+        sum += udeb_shx(mask, sum, 1);
+        sum += udeb_shx(mask, sum, 2);
         cum_t = sum;
     }
     const R cumt_2x = P[U_ECS] * P[U_FB_PERIOD];
@@ -421,78 +430,101 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         const R dz = P[U_DZ], dz_mix = P[U_MLD], dz1 = dz / R(2), conv = R(3155.76); // DIFFUSIVITY_CM2S_TO_M2YR
         const R c_mix = udeb_heat_capacity(dz_mix);
         y.cA = dt_sub / (dz * dz);
-        y.cA1 = dt_sub / (dz * dz1);
         y.cM = dt_sub / (dz_mix * dz1);
         y.dt_mix = dt_sub / dz_mix;
         y.dtdz = dt_sub / dz;
         y.dt_cmix = dt_sub / c_mix;
         y.kc = P[U_KAPPA] * conv;
         y.kmin = P[U_KAPPA_MIN] * conv;
+        if (!(y.kmin == y.kmin)) y.kmin = -R(RSCM_INF_F);
         y.dkdt_c = P[U_KAPPA_DKDT] * conv;
         y.pi_ratio = P[U_PI_RATIO];
-        y.tmax = P[U_TMAX];
+        y.tmax = (P[U_TMAX] == P[U_TMAX]) ? P[U_TMAX] : R(RSCM_INF_F);
+        y.kcA = y.kc * y.cA;
+        y.kminA = y.kmin * y.cA;
         y.lhc = lhc;
-        for (int h = 0; h < 2; ++h) {
-            const R f_l = (h == 0 ? fgnl : fgsl), f_o = R(0.5) - f_l;
-            const R denominator = f_o * (P[U_KLO] + f_l * lam_l);
-            y.tfb_dt[h] = S[US_AE0 + h] / c_mix * (lam_o + lam_l * P[U_KLO] * P[U_AMP] * f_l / denominator) * dt_sub;
-            y.famp[h] = R(1) + P[U_KLO] * f_l / denominator;
-            y.lhc_c[h] = lhc ? P[U_KLG] / (c_mix * f_o) * dt_sub : R(0);
-        }
+        const R f_l = (h == 0 ? fgnl : fgsl), f_o = R(0.5) - f_l;
+        const R denominator = f_o * (P[U_KLO] + f_l * lam_l);
+        y.tfb_dt = (h ? S[US_AE1] : S[US_AE0]) / c_mix * (lam_o + lam_l * P[U_KLO] * P[U_AMP] * f_l / denominator) * dt_sub;
+        y.famp = R(1) + P[U_KLO] * f_l / denominator;
+        y.lhc_c = lhc ? P[U_KLG] / (c_mix * f_o) * dt_sub : R(0);
     }
     const R gr_c0 = (lhc && !(fgnl < R(1e-15))) ? P[U_KLG] / (fgnl * c_ground) * dt_sub : R(0);
     const R gr_c1 = (lhc && !(fgsl < R(1e-15))) ? P[U_KLG] / (fgsl * c_ground) * dt_sub : R(0);
+    const UdebAir<R> air = udeb_air_constants(P);
+    // efficacy scaling of the forcing (apply_efficacy_and_qfrac, mod.rs:253-270) and the land-box denominators are
+    // constant over the year
+    R e_scale = R(1);
+    {
+        const int mode = static_cast<int>(P[U_EFF_APPLY]);
+        if (mode == 1) e_scale = P[U_EFF_CO2];
+        else if (mode == 2 && (co2_eff - co2_eff) == R(0) && co2_eff > R(0)) e_scale = P[U_EFF_CO2] / co2_eff;
+    }
+    const R kla = P[U_KLO] * P[U_AMP];
+    const R inv_den_n = R(1) / (lam_l * fgnl + P[U_KLO]), inv_den_s = R(1) / (lam_l * fgsl + P[U_KLO]);
     const R inv_steps = R(1) / steps;
     const R hx_c0 = (fgno > R(1e-15)) ? P[U_KNS] / fgno : R(0), hx_c1 = (fgso > R(1e-15)) ? P[U_KNS] / fgso : R(0);
     const R w0 = P[U_W0], fv = P[U_WVAR], wmin = w0 * (R(1) - fv);
+    const R wmin_b = (wmin == wmin) ? wmin : -R(RSCM_INF_F);
     const R inv_wt_nh = R(1) / P[U_WT_NH], inv_wt_sh = R(1) / P[U_WT_SH];
+    R sst_nh = R(0), sst_sh = R(0);
     for (int step = 1; step <= steps_n; ++step) {
         const R frac = R(step) * inv_steps;
         const R erf = erf_start + frac * (erf_end - erf_start);
-        R forcing[4];
-        udeb_apply_efficacy(P, S, erf, co2_eff, forcing);
+        const R e = (e_scale == R(1)) ? erf : erf * e_scale;
         if (lhc) {
             if (!(fgnl < R(1e-15))) S[US_GR0] += gr_c0 * (S[US_LAND0] - S[US_GR0]);
             if (!(fgsl < R(1e-15))) S[US_GR1] += gr_c1 * (S[US_LAND1] - S[US_GR1]);
         }
-        udeb_step_both(y, P, S, ctab, n, col, cp, cs, forcing[0], forcing[2]);
-        const R air_nho = udeb_sst_to_air(P, col[0]), air_sho = udeb_sst_to_air(P, col[BLOCK]);
-        S[US_LAND0] = udeb_land_temperature(P, air_nho, forcing[1], fgnl, lam_l);
-        S[US_LAND1] = udeb_land_temperature(P, air_sho, forcing[3], fgsl, lam_l);
+        udeb_substep<R, N>(y, P, S, tab, bottom, h, mask, T, F, e * (h ? S[US_QF2] : S[US_QF0]));
+        sst_nh = __shfl_sync(mask, T[0], quad);
+        sst_sh = __shfl_sync(mask, T[0], quad + 1);
+        const R air_nho = udeb_sst_to_air(air, sst_nh), air_sho = udeb_sst_to_air(air, sst_sh);
+        // calculate_land_temperature (mod.rs:352-375) with the year's reciprocal denominators
+        S[US_LAND0] = udeb_cap((e * S[US_QF1] * fgnl + kla * air_nho) * inv_den_n, y.tmax);
+        S[US_LAND1] = udeb_cap((e * S[US_QF3] * fgsl + kla * air_sho) * inv_den_s, y.tmax);
         if (fgno > R(1e-15)) S[US_HX0] = hx_c0 * (air_sho - air_nho);
         if (fgso > R(1e-15)) S[US_HX1] = hx_c1 * (air_nho - air_sho);
         const R gt = air_nho * fgno + S[US_LAND0] * fgnl + air_sho * fgso + S[US_LAND1] * fgsl;
-        S[US_W0] = r_max(w0 * (R(1) - fv * r_min(gt * inv_wt_nh, R(1))), wmin);
-        S[US_W1] = r_max(w0 * (R(1) - fv * r_min(gt * inv_wt_sh, R(1))), wmin);
+        S[US_W0] = udeb_floor(w0 * (R(1) - fv * udeb_cap(gt * inv_wt_nh, R(1))), wmin_b);
+        S[US_W1] = udeb_floor(w0 * (R(1) - fv * udeb_cap(gt * inv_wt_sh, R(1))), wmin_b);
     }
-    const R sst_nh = col[0], sst_sh = col[BLOCK];
-    S[US_AE0] = (r_abs(sst_nh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(P, sst_nh) / sst_nh;
-    S[US_AE1] = (r_abs(sst_sh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(P, sst_sh) / sst_sh;
-    const R st[4] = {udeb_sst_to_air(P, sst_nh), S[US_LAND0], udeb_sst_to_air(P, sst_sh), S[US_LAND1]};
+    if (steps_n < 1) { // (rejected by the host; keeps sst defined)
+        sst_nh = __shfl_sync(mask, T[0], quad);
+        sst_sh = __shfl_sync(mask, T[0], quad + 1);
+    }
+    S[US_AE0] = (r_abs(sst_nh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(air, sst_nh) / sst_nh;
+    S[US_AE1] = (r_abs(sst_sh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(air, sst_sh) / sst_sh;
+    const R st[4] = {udeb_sst_to_air(air, sst_nh), S[US_LAND0], udeb_sst_to_air(air, sst_sh), S[US_LAND1]};
     const R gt = st[0] * fgno + st[1] * fgnl + st[2] * fgso + st[3] * fgsl;
-    cx.scratch[static_cast<long long>(nr.scr + 2 * UDEB_MAXL + nhist) * cx.runs] = static_cast<double>(gt * dt_year);
+    if (q == 0) cx.scratch[static_cast<long long>(nr.scr + nhist) * cx.runs] = static_cast<double>(gt * dt_year);
+    __syncwarp(mask); // next year the other lanes of the quad read this entry
     S[US_NHIST] = R(nhist + 1);
     R f_end[4];
     udeb_apply_efficacy(P, S, erf_end, co2_eff, f_end);
     {
         const R lams[4] = {lam_o, lam_l, lam_o, lam_l};
-        R q = R(0), fb = R(0);
-        for (int i = 0; i < 4; ++i) { q += area[i] * f_end[i]; fb += area[i] * lams[i] * st[i]; }
-        out[0] = q - fb;
+        R qq = R(0), fb = R(0);
+        for (int i = 0; i < 4; ++i) { qq += area[i] * f_end[i]; fb += area[i] * lams[i] * st[i]; }
+        out[0] = qq - fb;
     }
     {
+        // ocean heat content: every lane weighs its rows (the mixed layer is the top lanes' row 0), the quad adds up
         const R rho_c = R(1026.0) * R(3985.0);
-        R total = R(0);
-        for (int h = 0; h < 2; ++h) {
-            const R *T = col + h * BLOCK;
-            total += rho_c * P[U_MLD] * T[0];
-            for (int l = 1; l < n; ++l) total += rho_c * P[U_DZ] * T[l * UDEB_ROW];
+        R part = R(0);
+        if (NB > NT) {
+            if (bottom) part = T[NB - 1];
         }
-        out[1] = total / R(2);
+#pragma unroll
+        for (int j = NT - 1; j >= 1; --j) part += T[j];
+        part = rho_c * P[U_DZ] * part + rho_c * (bottom ? P[U_DZ] : P[U_MLD]) * T[0];
+        part += udeb_shx(mask, part, 1);
+        part += udeb_shx(mask, part, 2);
+        out[1] = part / R(2);
     }
     out[2] = (sst_nh + sst_sh) / R(2);
     for (int i = 0; i < 4; ++i) out[3 + i] = st[i];
-    return true;
+    return ok;
 }
 
 } // namespace rscm_dev

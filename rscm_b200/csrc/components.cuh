@@ -32,6 +32,8 @@ template <class R> struct StepCtx {
     long long runs, run;
     int Tpad;
     int N;                // current time index
+    int role;             // lane of this thread within its member's lane group (0 when Prog::LANES == 1)
+    unsigned mask;        // the warp's lanes that step (shuffle mask for lane groups)
 };
 
 // Per-node literals the emitter passes: RK4 table row, offsets into ctab / sm / scratch / gtab, and one

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -72,6 +73,7 @@ struct rscm_b200_ensemble {
     const AotEntry *prog = nullptr;
     bool use_jit = false; // program compiled at run time (jit.cpp) instead of taken from the AOT registry
     std::string jit_cubin[3], jit_names[3]; // per kernel variant (write / logpost / both), compiled on first use
+    std::string jit_spec;                   // binding specialisation the loaded variants were compiled for (binding_spec)
     rscm::JitProgram jit;
     std::string err;
     int Tpad = 0;
@@ -211,6 +213,31 @@ size_t smem_bytes(const rscm_b200_ensemble *h, bool logp)
     return b;
 }
 
+// Run-time compiled programs are specialised on the parameter binding: a slot that no column feeds is a literal of the
+// program instead of a register loaded through the kernel's slot table.  The MAGICC kinds carry dozens of parameters per
+// component of which an ensemble varies a handful; without this every one of them is a live per-thread value (config 4:
+// 107 doubles, spilled to local memory).  The text is appended to the emitted `Prog` body, so the disk cache keys on it.
+std::string binding_spec(const rscm_b200_ensemble *h)
+{
+    const rscm::Graph &g = h->g;
+    for (int i = 0; i < g.n_slots; ++i)
+        if (!std::isfinite(g.slot_default[i])) return std::string(); // literals cannot carry NaN / inf: stay generic
+    std::string s = "    static constexpr bool SPECIALIZED = true;\n    __host__ __device__ static constexpr bool bound_slot(int i) { return ";
+    for (int i = 0; i < g.n_slots; ++i)
+        if (h->slot_col[i] >= 0) s += "i == " + std::to_string(i) + " || ";
+    s += "false; }\n    __host__ __device__ static constexpr double slot_value(int i) { return ";
+    char buf[64];
+    for (int i = 0; i < g.n_slots; ++i) {
+        if (h->slot_col[i] >= 0 || g.slot_default[i] == 0.0) continue;
+        std::snprintf(buf, sizeof buf, "%.17g", g.slot_default[i]);
+        std::string lit = buf;
+        if (lit.find_first_of(".eEn") == std::string::npos) lit += ".0";
+        s += "i == " + std::to_string(i) + " ? " + lit + " : ";
+    }
+    s += "0.0; }\n";
+    return s;
+}
+
 // What a launch that evaluates a member block of a larger ensemble in place needs beyond the plain arguments.
 struct LaunchOpts {
     int64_t ld_col = 0; // layout 0: leading dimension of the parameter matrix (0 = M)
@@ -316,7 +343,8 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
         a.init_def[c] = var.has_initial ? var.initial : std::numeric_limits<double>::quiet_NaN();
         a.out_off[c] = (write && h->out_base[c] >= 0) ? static_cast<long long>(h->out_base[c]) * a.runs * 8 : -1;
     }
-    const dim3 grid(static_cast<unsigned>((M + rscm_dev::BLOCK - 1) / rscm_dev::BLOCK), static_cast<unsigned>(S));
+    const int64_t members_per_cta = rscm_dev::BLOCK / g.lanes; // Prog::LANES threads work on one member
+    const dim3 grid(static_cast<unsigned>((M + members_per_cta - 1) / members_per_cta), static_cast<unsigned>(S));
     if (logp && d_summary) {
         const int64_t nb = static_cast<int64_t>(grid.x) * grid.y;
         if (nb > h->partials_capacity) {
@@ -354,10 +382,19 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     }
     if (h->use_jit) {
         const int variant = (write && !logp) ? 0 : ((!write && logp) ? 1 : 2);
+        const std::string spec = binding_spec(h);
+        if (spec != h->jit_spec) { // the binding changed: the loaded variants were specialised for another one
+            if (capturing) return fail(h, RSCM_B200_EINVAL, "program would have to be recompiled inside a stream capture");
+            cudaDeviceSynchronize();
+            rscm::jit_unload(h->jit);
+            for (int v = 0; v < 3; ++v) { h->jit_cubin[v].clear(); h->jit_names[v].clear(); }
+            h->jit_spec = spec;
+        }
         if (!h->jit.fn[variant]) { // first use of this kernel variant: compile (disk-cached) and load it
+            if (capturing) return fail(h, RSCM_B200_EINVAL, "program would have to be compiled inside a stream capture");
             std::string jerr;
             if (h->jit_cubin[variant].empty() &&
-                !rscm::jit_compile_cubin(g.program_source, h->dtype, variant, h->jit_cubin[variant], h->jit_names[variant], jerr))
+                !rscm::jit_compile_cubin(g.program_source + spec, h->dtype, variant, h->jit_cubin[variant], h->jit_names[variant], jerr))
                 return fail(h, RSCM_B200_EUNSUPPORTED, "run-time compilation failed: " + jerr);
             if (!rscm::jit_load(h->jit_cubin[variant], h->jit_names[variant], variant, h->jit, jerr))
                 return fail(h, RSCM_B200_ECUDA, "loading the run-time compiled program failed: " + jerr);
@@ -474,12 +511,18 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
         std::string jerr;
         // the plain `write` variant is compiled now (a program that does not compile is refused at creation, also for
         // host-only handles); the log-posterior variants follow on first use
-        if (!rscm::jit_compile_cubin(g.program_source, h->dtype, 0, h->jit_cubin[0], h->jit_names[0], jerr)) {
+        // Device handles compile on first use, specialised on the parameter binding (binding_spec); a host-only handle
+        // (and RSCM_B200_EAGER_JIT=1) compiles the unspecialised program now, so that a graph whose program does not
+        // compile is refused at creation.
+        if ((desc->device == -2 || std::getenv("RSCM_B200_EAGER_JIT")) &&
+            !rscm::jit_compile_cubin(g.program_source, h->dtype, 0, h->jit_cubin[0], h->jit_names[0], jerr)) {
             delete h;
             return fail(nullptr, RSCM_B200_EUNSUPPORTED,
                         "no ahead-of-time device program for this component graph and run-time compilation failed "
                         "(there is no CPU fallback): " + jerr);
         }
+        h->jit_cubin[0].clear();
+        h->jit_names[0].clear();
         h->use_jit = true;
     }
     h->Tpad = (g.T + 3) & ~3;
@@ -508,14 +551,7 @@ int rscm_b200_ensemble_create(const rscm_b200_graph_desc *desc, rscm_b200_ensemb
         }
     }
     cudaGetDevice(&h->device);
-    if (h->use_jit) {
-        cudaFree(nullptr); // make the primary context current for the driver-API module load
-        std::string jerr;
-        if (!rscm::jit_load(h->jit_cubin[0], h->jit_names[0], 0, h->jit, jerr)) {
-            delete h;
-            return fail(nullptr, RSCM_B200_ECUDA, "loading the run-time compiled program failed: " + jerr);
-        }
-    }
+    if (h->use_jit) cudaFree(nullptr); // make the primary context current for the driver-API module loads
 
     // RK4 sub-step tables
     if (g.n_rk > 0) {
@@ -616,7 +652,14 @@ int rscm_b200_variable_source(const rscm_b200_ensemble *h, int component, const 
         if (n.in_var[i] == v) return n.in_src[i];
     return -1;
 }
-const char *rscm_b200_program_signature(const rscm_b200_ensemble *h) { return h->g.signature.c_str(); }
+const char *rscm_b200_program_signature(const rscm_b200_ensemble *h)
+{
+    if (!h->use_jit) return h->g.signature.c_str();
+    // run-time compiled programs: the text that is compiled, i.e. with the current binding specialisation
+    thread_local std::string text;
+    text = h->g.program_source + binding_spec(h);
+    return text.c_str();
+}
 int rscm_b200_program_is_jit(const rscm_b200_ensemble *h) { return h->use_jit ? 1 : 0; }
 int rscm_b200_time_index(const rscm_b200_ensemble *h, double time) { return rscm::time_index_for(h->g, time); }
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -75,13 +76,31 @@ static std::vector<double> udeb_const_table(const std::vector<double> &p, std::s
     }
     const double total_depth = mld + (static_cast<double>(n) - 1.0) * dz;
     for (int l = 0; l < n; ++l) t[5 * n + l] = 1.0 - (mld + static_cast<double>(l) * dz) / total_depth;
-    // device layout: layer-major, per layer {af_top, af_bottom, af_diff, omr_l, g_nh, g_sh, omr_{l-1}, 0}
-    // (climate_udeb.cuh UDEB_CT = 8: 64-byte rows, 128-bit shared-memory loads)
-    std::vector<double> r(8 * n, 0.0);
-    static const int order[6] = {0, 1, 2, 5, 3, 4};
-    for (int l = 0; l < n; ++l) {
-        for (int k = 0; k < 6; ++k) r[8 * l + k] = t[order[k] * n + l];
-        r[8 * l + 6] = l > 0 ? t[5 * n + l - 1] : 0.0;
+    // device layout (climate_udeb.cuh): one table per lane role q = 2*end + hemisphere, UDEB_MAXR = 25 rows of
+    // UDEB_CT = 6 doubles in SWEEP order (top sweep: row j = layer j; bottom sweep: row j = layer n-1-j):
+    //   {near area, far area, af_diff, g_h, omr, af_top}
+    // near / far = area factor of the coupling towards the previous / next row of the sweep (top: af_top x dz/dz_up and
+    // af_bottom; bottom: the other way round; dz/dz_up = 2 for layer 1 — the half layer below the mixed layer — when it is
+    // an interior layer); omr = relative-depth factor of the diffusivity the row has to compute (top: boundary below the
+    // layer; bottom: boundary above it).  Row 0 of a role is the end row of the column: it uses af_top, af_bottom (far), g, omr.
+    const int k = (n - 2) >> 1;
+    std::vector<double> r(4 * 25 * 6, 0.0);
+    for (int q = 0; q < 4; ++q) {
+        const int h = q & 1;
+        const bool bottom = (q & 2) != 0;
+        const int nrows = bottom ? n - k - 1 : k + 1;
+        for (int j = 0; j < nrows; ++j) {
+            const int l = bottom ? n - 1 - j : j;
+            double *row = &r[(q * 25 + j) * 6];
+            const double at = t[l], ab = t[n + l], ad = t[2 * n + l], g = t[(3 + h) * n + l];
+            const double at_up = at * ((l == 1 && l != n - 1) ? 2.0 : 1.0);
+            row[0] = bottom ? ab : at_up;
+            row[1] = bottom ? at_up : ab;
+            row[2] = ad;
+            row[3] = g;
+            row[4] = bottom ? (l > 0 ? t[5 * n + l - 1] : 0.0) : t[5 * n + l];
+            row[5] = at;
+        }
     }
     return r;
 }
@@ -278,9 +297,10 @@ static const std::vector<KindInfo> &kinds()
          1, -2,
          // geometry / switches are per-graph (they size the shared-memory layout and the host-computed tables)
          {0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 1},
-         96, /*n_state*/ 19, /*n_smem*/ 100, /*scratch_per_T*/ 1, /*needs_time*/ true,
+         96, /*n_state: 19 scalars + this lane's 25 rows of the ocean column*/ 44, /*n_smem: eliminated off-diagonal of those rows*/ 25, /*scratch_per_T*/ 1, /*needs_time*/ true,
          /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table, nullptr,
-         /*aux_param*/ -1, /*scratch_fixed: c' columns of both hemispheres*/ 100},
+         /*aux_param: n_layers sizes the register rows*/ 0, /*scratch_fixed*/ 0, /*no_slots*/ false, /*lanes: 2 hemispheres x 2 sweep ends*/ 4,
+         /*aux_template*/ true},
         {RSCM_B200_FOUR_BOX_OHU, "FourBoxOceanHeatUptake", "four_box_ohu",
          // crates/rscm-components/src/components/four_box_ocean_heat_uptake.rs
          {{"Effective Radiative Forcing|Aggregated", REQ_INPUT, RSCM_B200_SCALAR}, {"Heat Uptake|Ocean", REQ_OUTPUT, RSCM_B200_FOUR_BOX}},
@@ -480,12 +500,16 @@ static void emit_program(Graph &g)
     // 8 CTAs of 128 threads per SM = 64 registers per thread; register-hungry programs get 4 (128 registers)
     // programs with per-thread shared-memory scratch are limited by shared memory, not registers (2 = no register cap;
     // two CTAs fit one SM in fp32)
-    o << "    static constexpr int MIN_BLOCKS = " << (g.n_smem > 0 ? 2 : (weight <= 32 ? 8 : 4)) << ";\n";
+    // programs whose members span several lanes keep rows of state in registers: 3 CTAs = 168 registers per thread
+    int lanes_blocks = 3;
+    if (const char *e = std::getenv("RSCM_B200_LANES_MIN_BLOCKS")) lanes_blocks = std::max(1, std::min(8, std::atoi(e))); // tuning knob
+    o << "    static constexpr int MIN_BLOCKS = " << (g.lanes > 1 ? lanes_blocks : (g.n_smem > 0 ? 2 : (weight <= 32 ? 8 : 4))) << ";\n";
     o << "    static constexpr int NS = " << g.n_state << ";\n";
     o << "    static constexpr int NSM = " << g.n_smem << ";\n";
+    o << "    static constexpr int LANES = " << g.lanes << ";\n";
     o << "    static constexpr bool NEEDS_TIME = " << (g.needs_time ? "true" : "false") << ";\n";
     // exogenous rows are staged into shared memory unless per-thread scratch or a long row list needs the space
-    g.stage_exo = g.n_smem == 0 && g.n_exo_rows <= 24;
+    g.stage_exo = (g.n_smem == 0 || g.lanes > 1) && g.n_exo_rows <= 24;
     o << "    static constexpr bool STAGE_EXO = " << (g.stage_exo ? "true" : "false") << ";\n";
     o << "    __host__ __device__ static constexpr int exo_row(int c) { return ";
     for (int c = 0; c < g.n_cells; ++c) {
@@ -541,7 +565,7 @@ static void emit_program(Graph &g)
         if (n.kind == KIND_AGGREGATOR) continue;
         const KindInfo *k = kind_info(n.kind);
         if (k->n_state == 0 && k->n_smem == 0) continue;
-        o << "        rscm_dev::" << k->dev_name << "_init_state<R>(P + " << n.param_base << ", D + " << n.derived_base << ", S + "
+        o << "        rscm_dev::" << k->dev_name << "_init_state<R" << (k->aux_template ? ", " + std::to_string(n.aux) : std::string()) << ">(P + " << n.param_base << ", D + " << n.derived_base << ", S + "
           << n.state_base << ", cx, " << node_ref(n) << ");\n";
     }
     o << "    }\n";
@@ -608,7 +632,7 @@ static void emit_program(Graph &g)
             if (in_exprs.empty()) o << "R(0)";
             o << "};\n";
             o << "        R out[" << n_out_vals << "];\n";
-            o << "        if (rscm_dev::" << k->dev_name << "_solve<R>(P + " << n.param_base << ", D + " << n.derived_base
+            o << "        if (rscm_dev::" << k->dev_name << "_solve<R" << (k->aux_template ? ", " + std::to_string(n.aux) : std::string()) << ">(P + " << n.param_base << ", D + " << n.derived_base
               << ", in, out, cx, S + " << n.state_base << ", " << node_ref(n) << ")) {\n";
             int pos = 0;
             for (size_t i = 0; i < n.out_var.size(); ++i) {
@@ -907,6 +931,7 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         n.ctab_base = static_cast<int>(g.ctab.size());
         g.n_state += k->n_state;
         g.n_smem += k->n_smem;
+        g.lanes = std::max(g.lanes, k->lanes);
         g.n_scratch_rows += k->scratch_fixed + k->scratch_per_T * g.T;
         g.needs_time = g.needs_time || k->needs_time;
         if (k->const_table) {

@@ -50,6 +50,8 @@ struct KindInfo {
     int aux_param = -1; // index of an integer parameter handed to the device code as a compile-time literal
     int scratch_fixed = 0; // global scratch rows that do not scale with the run length (come first in the node's rows)
     bool no_slots = false; // all parameters are per-graph and only feed const_table: they take no kernel parameter slots
+    int lanes = 1; // lanes of a warp that work on one member (ClimateUDEB: 4); the program takes the largest of its kinds
+    bool aux_template = false; // the aux literal is also a template argument of <dev_name>_solve / _init_state
 };
 
 const KindInfo *kind_info(int kind);
@@ -93,6 +95,7 @@ struct Graph {
     std::vector<int> order;     // node ids in execution order
     std::vector<int> exo_vars;  // variable ids, scenario order
     int n_cells = 0, n_slots = 0, n_derived = 0, n_exo_rows = 0, n_rk = 0;
+    int lanes = 1;         // Prog::LANES: threads per member
     bool stage_exo = true; // Prog::STAGE_EXO: exogenous rows staged in shared memory (else read from global)
     int n_state = 0, n_smem = 0, n_scratch_rows = 0; // stateful components: totals (scratch rows already x T)
     bool needs_time = false;

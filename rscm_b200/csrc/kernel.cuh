@@ -195,6 +195,19 @@ __device__ __forceinline__ void obs_accumulate(const KArgs &a, const double *s_o
     }
 }
 
+// Binding specialisation (engine.cu: binding_spec): a run-time compiled program may state which parameter slots are fed by
+// a column; the others are literals.  Ahead-of-time programs carry no such statement and keep the run-time slot table.
+template <class Prog, class = void> struct ProgSpec {
+    static constexpr bool on = false;
+    __host__ __device__ static constexpr bool bound(int) { return true; }
+    __host__ __device__ static constexpr double value(int) { return 0.0; }
+};
+template <class Prog> struct ProgSpec<Prog, decltype(void(Prog::SPECIALIZED))> {
+    static constexpr bool on = true;
+    __host__ __device__ static constexpr bool bound(int i) { return Prog::bound_slot(i); }
+    __host__ __device__ static constexpr double value(int i) { return Prog::slot_value(i); }
+};
+
 template <class R, class Prog, bool WRITE, bool LOGP>
 __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::MIN_BLOCKS - 1 : Prog::MIN_BLOCKS) ensemble_kernel(const __grid_constant__ KArgs a)
 {
@@ -238,16 +251,24 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     }
 
     // ---- per-member parameters (coalesced SoA loads overlap the bulk copies) ----
-    const long long m_raw = static_cast<long long>(blockIdx.x) * BLOCK + threadIdx.x;
+    // Prog::LANES lanes work on one member (ClimateUDEB: 4, see climate_udeb.cuh); a CTA then holds BLOCK / LANES members
+    constexpr int LANES = Prog::LANES;
+    const int role = LANES == 1 ? 0 : static_cast<int>(threadIdx.x) % LANES;
+    const long long m_raw = static_cast<long long>(blockIdx.x) * (BLOCK / LANES) + threadIdx.x / LANES;
     const bool active = m_raw < a.M;
+    const bool writer = active && role == 0; // the lane that stores the member's outputs
+    const unsigned step_mask = __ballot_sync(0xffffffffu, active);
     const long long m = active ? m_raw : a.M - 1;
     const long long run = static_cast<long long>(blockIdx.y) * a.M + m;
     const double *pm = a.params + m * a.ld_mem;
 
     R P[NP > 0 ? NP : 1];
 #pragma unroll
-    for (int i = 0; i < NP; ++i)
-        P[i] = a.slot_col[i] >= 0 ? static_cast<R>(__ldg(pm + a.slot_col[i] * a.ld_col)) : static_cast<R>(a.slot_def[i]);
+    for (int i = 0; i < NP; ++i) {
+        using Spec = ProgSpec<Prog>;
+        if (Spec::on) P[i] = Spec::bound(i) ? static_cast<R>(__ldg(pm + a.slot_col[i] * a.ld_col)) : static_cast<R>(Spec::value(i));
+        else P[i] = a.slot_col[i] >= 0 ? static_cast<R>(__ldg(pm + a.slot_col[i] * a.ld_col)) : static_cast<R>(a.slot_def[i]);
+    }
     R D[ND > 0 ? ND : 1];
     Prog::template prepare<R>(P, D);
 
@@ -287,6 +308,8 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     cx.run = run;
     cx.Tpad = a.Tpad;
     cx.N = 0;
+    cx.role = role;
+    cx.mask = step_mask;
     R S[Prog::NS > 0 ? Prog::NS : 1];
     if (!LOGP || active) Prog::template init_state<R>(P, D, S, cx);
 
@@ -303,7 +326,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     char *p1 = reinterpret_cast<char *>(a.out) + run * 8, *p2 = p1, *p4 = p1;
     if (WRITE) {
         if (tnext == 0 && tnext < a.t_stop) {
-            if (active) {
+            if (writer) {
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
                     if (a.out_off[c] >= 0)
@@ -328,7 +351,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
 
         if (WRITE) {
             if (N + 1 == tnext && tnext < a.t_stop) { // block-uniform
-                if (active) {
+                if (writer) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
                         if (a.out_off[c] >= 0)
@@ -344,7 +367,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
         for (int c = 0; c < NC; ++c) cur[c] = nxt[c];
     }
 
-    if (a.status && active) {
+    if (a.status && writer) {
         bool nonfinite = false;
 #pragma unroll
         for (int c = 0; c < NC; ++c)
@@ -361,7 +384,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
         double post = lp + total;
         if (bad || !(fabs(lp) <= 1.7976931348623157e308)) post = -RSCM_INF;
         const long long lp_idx = static_cast<long long>(blockIdx.y) * a.lp_ld + m;
-        if (active) {
+        if (writer) {
             a.logpost[lp_idx] = post;
             // fused all-gather: 8 B per run straight into every peer's buffer over NVLink (a warp's stores of one peer
             // are one contiguous 256 B segment)
@@ -374,7 +397,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (a.summary) {
             // warp-shuffle + block reduction of the ensemble summary
-            const bool fin = active && (fabs(post) <= 1.7976931348623157e308);
+            const bool fin = writer && (fabs(post) <= 1.7976931348623157e308);
             double vmax = fin ? post : -RSCM_INF;
             long long amax = fin ? run : -1;
             double vsum = fin ? post : 0.0;
