@@ -110,13 +110,13 @@ template <class R> __device__ inline bool udeb_lamcalc(const R *P, R ecs, R &lam
         const R lam_l = lam + fratio * (lam - lam_o) / rlo;
         const R B1 = fgnl * lam_l + k_lo, B3 = fgsl * lam_l + k_lo;
         if (r_abs(B1) < R(1e-15) || r_abs(B3) < R(1e-15)) return false;
-        const R r1 = R(1) / B1, r3 = R(1) / B3;
+        const R r1 = r_rcp(B1), r3 = r_rcp(B3); // |B| >= 1e-15 checked above, far from the subnormal range
         const R a00 = fgno * lam_o + kla + k_ns - k_lo * kla * r1;
         const R a22 = fgso * lam_o + kla + k_ns - k_lo * kla * r3;
         const R g0 = f0 + k_lo * f1 * r1, g2 = f2 + k_lo * f3 * r3;
         const R det = a00 * a22 - k_ns * k_ns;
         if (r_abs(det) < R(1e-15)) return false;
-        const R rd = R(1) / det;
+        const R rd = r_rcp(det);
         const R t0 = (g0 * a22 + k_ns * g2) * rd, t2 = (a00 * g2 + k_ns * g0) * rd;
         const R t1 = (f1 + kla * t0) * r1, t3 = (f3 + kla * t2) * r3;
         const R ocean_mean = (fgno * t0 + fgso * t2) * inv_o;
@@ -246,8 +246,21 @@ template <class R> __device__ __forceinline__ R udeb_shx(unsigned mask, R v, int
 // f64::max(x, lo) / f64::min(x, hi) for a bound that is not NaN (the year set-up replaces a NaN bound by -inf / +inf,
 // which is what the NaN-ignoring f64::max / min make of it): one compare and a select instead of the library fmax / fmin
 // (compare, NaN quieting, selects: eight instructions).  A NaN x yields the bound, as f64::max / min do.
-template <class R> __device__ __forceinline__ R udeb_floor(R x, R lo) { return x > lo ? x : lo; }
-template <class R> __device__ __forceinline__ R udeb_cap(R x, R hi) { return x < hi ? x : hi; }
+// (written as setp + selp: the compiler turns the C++ conditional back into the fmax / fmin pattern)
+__device__ __forceinline__ double udeb_floor(double x, double lo)
+{
+    double r;
+    asm("{\n.reg .pred p;\nsetp.gt.f64 p, %1, %2;\nselp.f64 %0, %1, %2, p;\n}" : "=d"(r) : "d"(x), "d"(lo));
+    return r;
+}
+__device__ __forceinline__ double udeb_cap(double x, double hi)
+{
+    double r;
+    asm("{\n.reg .pred p;\nsetp.lt.f64 p, %1, %2;\nselp.f64 %0, %1, %2, p;\n}" : "=d"(r) : "d"(x), "d"(hi));
+    return r;
+}
+__device__ __forceinline__ float udeb_floor(float x, float lo) { return x > lo ? x : lo; }
+__device__ __forceinline__ float udeb_cap(float x, float hi) { return x < hi ? x : hi; }
 
 // One sub-step of step_hemisphere for this lane's half-sweep.
 //
@@ -285,13 +298,12 @@ __device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, c
     const R tul = w * y.dtdz;
     const R pt0 = y.pi_ratio * tul * t0;
     const R u_n = bottom ? tul : R(0), u_f = bottom ? R(0) : tul;
-    // Division-free elimination.  With q_j = product of the pivots up to row j (q_{-1} = 1) the sweep
-    //     pivot_j = b_j - near_j f_{j-1},   f_j = far_j / pivot_j,   d'_j = (d_j + near_j d'_{j-1}) / pivot_j
-    // becomes three LINEAR recurrences
-    //     g_j = far_j q_{j-1},   q_j = b_j q_{j-1} - near_j g_{j-1},   D_j = d_j q_{j-1} + near_j D_{j-1},
-    // with f_j = g_j / q_j and d'_j = D_j / q_j.  The loop-carried dependence is one FMA per row (q) instead of an FMA, a
-    // reciprocal and a multiply; the 25 reciprocals no longer depend on each other, so a warp overlaps them.  Same
-    // numbers up to rounding; the pivots of this system lie between 1 and a few units, so q stays far inside the range.
+    // The loop-carried chain of the sweep is pivot (FMA) -> reciprocal (MUFU + 3 FMA) -> f (MUL): about 57 cycles per row
+    // at the measured 8-cycle DFMA and 17-cycle MUFU.RCP64H latencies (tools/micro/fp64_latency.cu), which three warps per
+    // scheduler cover.  UDEB_DIVISION_FREE selects an alternative with three LINEAR recurrences over q_j = product of the
+    // pivots (g_j = far_j q_{j-1}, q_j = b_j q_{j-1} - near_j g_{j-1}, D_j = d_j q_{j-1} + near_j D_{j-1}; f_j = g_j / q_j,
+    // d'_j = D_j / q_j): one FMA in the chain, independent reciprocals — but five more FP64 instructions per row, and the
+    // kernel is bound by issue slots, not by latency: measured 1.90e8 against 1.98e8 member-years/s for the chained form.
     R carry, q1, g1, D1, fp, dp;
     {
         const UdebRow<R> c = udeb_row<R>(tab);
@@ -323,12 +335,19 @@ __device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, c
         const R far = (knew + u_f) * c.af;
         const R bi = (R(1) + near) + (far + tul * c.ad);
         const R di = T[j] + pt0 * c.ad + dwc * c.g;
+#ifndef UDEB_DIVISION_FREE
+        const R r = r_rcp(bi - near * fp);
+        fp = far * r;
+        dp = (di + near * dp) * r;
+        const R g = fp, q = R(1), D = dp;
+#else
         const R g = far * q1;
         const R q = bi * q1 - near * g1;
         const R D = di * q1 + near * D1;
         const R r = r_rcp(q);
         fp = g * r;
         dp = D * r;
+#endif
         F[j * BLOCK] = fp;
         T[j] = dp;
         carry = knew;
@@ -392,13 +411,20 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         // Which entries the window covers follows from the time axis alone (shared memory, block-uniform): entries
         // [first, nhist) count fully, entry first-1 with weight `partial` if the window ends inside it.  Each lane of
         // the quad sums every fourth entry, newest first, with independent loads; the quad adds the partial sums.
-        R rem = P[U_FB_PERIOD], partial = R(0);
+        R partial = R(0);
         int first = nhist;
-        for (int i = nhist - 1; i >= 0; --i) {
-            if (rem <= R(0)) break;
-            const R dt = R(cx.bounds[i + 1] - cx.bounds[i]);
-            if (dt <= rem) { first = i; rem -= dt; }
-            else { partial = rem / dt; rem = R(0); }
+        const double *win = cx.gtab + nr.gt; // host-computed window per step for the graph's period (graph.cpp)
+        if (static_cast<double>(P[U_FB_PERIOD]) == win[0]) {
+            first = static_cast<int>(win[2 + 2 * nhist]);
+            partial = R(win[3 + 2 * nhist]);
+        } else { // period bound per member: walk the axis
+            R rem = P[U_FB_PERIOD];
+            for (int i = nhist - 1; i >= 0; --i) {
+                if (rem <= R(0)) break;
+                const R dt = R(cx.bounds[i + 1] - cx.bounds[i]);
+                if (dt <= rem) { first = i; rem -= dt; }
+                else { partial = rem / dt; rem = R(0); }
+            }
         }
         const double *hist = cx.scratch + static_cast<long long>(nr.scr) * cx.runs;
         R sum = R(0);
@@ -412,7 +438,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     const R cumt_2x = P[U_ECS] * P[U_FB_PERIOD];
     const R cumt_factor = (r_abs(cumt_2x) > R(1e-15)) ? R(1) + P[U_FB_CUMT] * (cum_t - cumt_2x) / cumt_2x : R(1);
     const R erf_mid = (erf_start + erf_end) / R(2);
-    const R q_factor = R(1) + P[U_FB_Q] * (r_max(erf_mid, R(0)) - P[U_RF2X]);
+    const R q_factor = R(1) + P[U_FB_Q] * (udeb_floor(erf_mid, R(0)) - P[U_RF2X]);
     const R aecs = P[U_ECS] * cumt_factor * q_factor;
 
     R lam_o = S[US_LAMO], lam_l = S[US_LAML], co2_eff = S[US_EFF];

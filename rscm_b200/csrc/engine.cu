@@ -359,6 +359,27 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
         a.ticket = h->d_ticket;
     }
 
+    if (h->use_jit) { // compile / load before the timing events: compilation is host time, not kernel time
+        const int variant = (write && !logp) ? 0 : ((!write && logp) ? 1 : 2);
+        const std::string spec = binding_spec(h);
+        if (spec != h->jit_spec) { // the binding changed: the loaded variants were specialised for another one
+            if (capturing) return fail(h, RSCM_B200_EINVAL, "program would have to be recompiled inside a stream capture");
+            cudaDeviceSynchronize();
+            rscm::jit_unload(h->jit);
+            for (int v = 0; v < 3; ++v) { h->jit_cubin[v].clear(); h->jit_names[v].clear(); }
+            h->jit_spec = spec;
+        }
+        if (!h->jit.fn[variant]) { // first use of this kernel variant: compile (disk-cached) and load it
+            if (capturing) return fail(h, RSCM_B200_EINVAL, "program would have to be compiled inside a stream capture");
+            std::string jerr;
+            if (h->jit_cubin[variant].empty() &&
+                !rscm::jit_compile_cubin(g.program_source + spec, h->dtype, variant, h->jit_cubin[variant], h->jit_names[variant], jerr))
+                return fail(h, RSCM_B200_EUNSUPPORTED, "run-time compilation failed: " + jerr);
+            if (!rscm::jit_load(h->jit_cubin[variant], h->jit_names[variant], variant, h->jit, jerr))
+                return fail(h, RSCM_B200_ECUDA, "loading the run-time compiled program failed: " + jerr);
+        }
+    }
+
     // CUDA-event timing of the fused kernel on its launch stream
     size_t ei = h->ev_next;
     if (capturing) {
@@ -382,23 +403,6 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     }
     if (h->use_jit) {
         const int variant = (write && !logp) ? 0 : ((!write && logp) ? 1 : 2);
-        const std::string spec = binding_spec(h);
-        if (spec != h->jit_spec) { // the binding changed: the loaded variants were specialised for another one
-            if (capturing) return fail(h, RSCM_B200_EINVAL, "program would have to be recompiled inside a stream capture");
-            cudaDeviceSynchronize();
-            rscm::jit_unload(h->jit);
-            for (int v = 0; v < 3; ++v) { h->jit_cubin[v].clear(); h->jit_names[v].clear(); }
-            h->jit_spec = spec;
-        }
-        if (!h->jit.fn[variant]) { // first use of this kernel variant: compile (disk-cached) and load it
-            if (capturing) return fail(h, RSCM_B200_EINVAL, "program would have to be compiled inside a stream capture");
-            std::string jerr;
-            if (h->jit_cubin[variant].empty() &&
-                !rscm::jit_compile_cubin(g.program_source + spec, h->dtype, variant, h->jit_cubin[variant], h->jit_names[variant], jerr))
-                return fail(h, RSCM_B200_EUNSUPPORTED, "run-time compilation failed: " + jerr);
-            if (!rscm::jit_load(h->jit_cubin[variant], h->jit_names[variant], variant, h->jit, jerr))
-                return fail(h, RSCM_B200_ECUDA, "loading the run-time compiled program failed: " + jerr);
-        }
         const int rc = rscm::jit_launch(h->jit, variant, grid.x, grid.y, rscm_dev::BLOCK, static_cast<unsigned>(smem_bytes(h, logp)), st, &a);
         if (rc != 0) return fail(h, RSCM_B200_ECUDA, "cuLaunchKernel failed with CUresult " + std::to_string(rc));
     } else {

@@ -105,9 +105,34 @@ static std::vector<double> udeb_const_table(const std::vector<double> &p, std::s
     return r;
 }
 
+// ClimateUDEB: the window of the cumulative-temperature feedback (adjusted_ecs, udeb/mod.rs:302-330).  At step N the
+// history holds one entry per completed step; walking it backwards with years_remaining = feedback_cumt_period, entries
+// [first, N) count fully and entry first-1 with weight `partial` when the window ends inside it.  Which entries those are
+// follows from the time axis and the period alone, in exactly this arithmetic, so the host states it once per graph:
+// {period, then per step N: first, partial}.  A member whose period differs (bound per member) walks the axis itself.
+static std::vector<double> udeb_window_table(const std::vector<double> &p, int n_times, const double *bounds, std::string &)
+{
+    const double period = p[15];
+    std::vector<double> t(2 + 2 * static_cast<size_t>(n_times), 0.0);
+    t[0] = period;
+    for (int n = 0; n < n_times; ++n) {
+        double rem = period, partial = 0.0;
+        int first = n;
+        for (int i = n - 1; i >= 0; --i) {
+            if (rem <= 0.0) break;
+            const double dt = bounds[i + 1] - bounds[i];
+            if (dt <= rem) { first = i; rem -= dt; }
+            else { partial = rem / dt; rem = 0.0; }
+        }
+        t[2 + 2 * n] = first;
+        t[3 + 2 * n] = partial;
+    }
+    return t;
+}
+
 // OceanCarbon: scaled impulse-response function by lag in months, irf(k/12) for k = 0 .. steps*(T-1)
 // (OceanCarbonParameters::irf / scale_irf, IrfForm::evaluate — crates/rscm-magicc/src/parameters/ocean_carbon.rs:99-130,378-397)
-static std::vector<double> ocean_irf_table(const std::vector<double> &p, int n_times, std::string &err)
+static std::vector<double> ocean_irf_table(const std::vector<double> &p, int n_times, const double *, std::string &err)
 {
     const int steps = static_cast<int>(p[10]);
     if (steps < 1 || steps > 16 || p[10] != steps) { err = "OceanCarbon: steps_per_year must be an integer in [1, 16]"; return {}; }
@@ -298,7 +323,7 @@ static const std::vector<KindInfo> &kinds()
          // geometry / switches are per-graph (they size the shared-memory layout and the host-computed tables)
          {0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 1},
          96, /*n_state: 19 scalars + this lane's 25 rows of the ocean column*/ 44, /*n_smem: eliminated off-diagonal of those rows*/ 25, /*scratch_per_T*/ 1, /*needs_time*/ true,
-         /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table, nullptr,
+         /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table, &udeb_window_table,
          /*aux_param: n_layers sizes the register rows*/ 0, /*scratch_fixed*/ 0, /*no_slots*/ false, /*lanes: 2 hemispheres x 2 sweep ends*/ 4,
          /*aux_template*/ true},
         {RSCM_B200_FOUR_BOX_OHU, "FourBoxOceanHeatUptake", "four_box_ohu",
@@ -943,7 +968,7 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         n.gtab_base = static_cast<int>(g.gtab.size());
         if (k->global_table) {
             std::string terr;
-            const std::vector<double> tab = k->global_table(n.params, g.T, terr);
+            const std::vector<double> tab = k->global_table(n.params, g.T, g.bounds.data(), terr);
             if (!terr.empty()) { err = terr; return false; }
             g.gtab.insert(g.gtab.end(), tab.begin(), tab.end());
         }

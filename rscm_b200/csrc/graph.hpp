@@ -46,7 +46,8 @@ struct KindInfo {
     // per-graph constant table computed on the host from the (non-bindable) geometry parameters
     std::vector<double> (*const_table)(const std::vector<double> &params, std::string &err) = nullptr;
     // large per-graph table kept in global memory (n_times is passed for tables sized by the run length)
-    std::vector<double> (*global_table)(const std::vector<double> &params, int n_times, std::string &err) = nullptr;
+    // (n_times and the time bounds [n_times + 1] are passed for tables sized by, or derived from, the time axis)
+    std::vector<double> (*global_table)(const std::vector<double> &params, int n_times, const double *bounds, std::string &err) = nullptr;
     int aux_param = -1; // index of an integer parameter handed to the device code as a compile-time literal
     int scratch_fixed = 0; // global scratch rows that do not scale with the run length (come first in the node's rows)
     bool no_slots = false; // all parameters are per-graph and only feed const_table: they take no kernel parameter slots

@@ -219,3 +219,37 @@ def test_gpu_matches_magicc7_golden_full_default(name, tmp_path, monkeypatch):
     model.run()
     t4 = np.asarray(model.timeseries().get_fourbox_timeseries_by_name("Surface Temperature").values())
     np.testing.assert_allclose(t4 @ AREA_W, expected, rtol=0.1, atol=1e-6, err_msg=name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [1, 7, 33, 130])
+def test_udeb_log_posterior_and_ragged_member_counts(M, tmp_path, monkeypatch):
+    """Four lanes work on one member (climate_udeb.cuh): the log-posterior variants (padding lanes stay for the block
+    reduction), the summary and ragged member counts — 1 member = one lane quad of a warp, 33 = one quad into a second CTA."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    from rscm_b200 import _ffi
+    years = np.arange(1850.0, 1921.0)
+    b = udeb_builder({}, years)
+    ens = b.build_ensemble().bind_parameters(UDEB_BINDS)
+    ramp = 3.71 * np.log2(np.exp(0.006 * (years - 1850.0)))
+    sc = ens.pack_scenarios([{"Effective Radiative Forcing": np.where(years >= 1851.0, 3.71, 0.0)}, {"Effective Radiative Forcing": ramp}])
+    p = _udeb_params(M, seed=9)
+    m = oracle_from_builder(b)
+    ob = oracle_bindings(b, UDEB_BINDS)
+    names = ["Sea Surface Temperature", "Heat Uptake", "Surface Temperature"]
+    ens.select_outputs(names)
+    got = ens.split_outputs(ens.run(p, sc))
+    ref = m.split(m.run_batch(ob, p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
+    obs = [("Sea Surface Temperature", float(y), 0.8, 0.3) for y in range(1860, 1921, 10)]
+    priors = [(_ffi.PRIOR_UNIFORM, 1.0, 5.0), (_ffi.PRIOR_NORMAL, 1.0, 0.5), (_ffi.PRIOR_UNIFORM, 1.0, 1.6), (_ffi.PRIOR_UNIFORM, 0.0, 0.45)]
+    ens.set_target(obs).set_priors(priors)
+    lp, summ = ens.log_posterior(p, sc, with_summary=True)
+    want = m.log_posterior_batch(ob, p, ens.exogenous_names, sc, priors, obs)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(lp), fin)
+    assert np.max(np.abs(lp[fin] - want[fin]) / np.abs(want[fin])) <= 1e-9 if fin.any() else True
+    assert summ["n_runs"] == 2 * M and summ["n_finite"] == int(fin.sum())
+    if fin.any():
+        assert summ["argmax"] == int(np.argmax(np.where(fin, lp, -np.inf))) and summ["max_logpost"] == lp[summ["argmax"]]
