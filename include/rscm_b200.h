@@ -312,6 +312,10 @@ double rscm_b200_kernel_ms(rscm_b200_ensemble *h, int reset);
  * throughput of `device` in TFLOP/s (2 flop per FMA) */
 int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops);
 
+/* Self-test hook: y[i] = exp(x[i]) (op 0) or log(x[i]) (op 1) with the engine's own fp64 device implementations
+ * (constant-bank coefficients; rscm_b200/csrc/components.cuh), so that their accuracy can be checked from the host. */
+int rscm_b200_device_math(int op, const double *d_x, int64_t n, double *d_y, void *stream);
+
 /* ---- ensemble sampler: the stretch move on the device ------------------------
  * Replaces the per-walker host loops of EnsembleSampler::update_group
  * (crates/rscm-calibrate/src/sampler/ensemble.rs:489-546) around the

@@ -15,6 +15,7 @@
 // ("hoisted" / "reciprocal"): those re-associations change results by O(1 ulp)
 // per operation, far inside the 1e-9 relative parity bar (fp64).
 #pragma once
+#include "math_tables.cuh"
 
 namespace rscm_dev {
 
@@ -42,11 +43,76 @@ struct NodeRef {
     int rk, ctab, sm, scr, gt, aux;
 };
 
+// ---------------------------------------------------------------------------
+// exp / log in fp64.  The CUDA library versions materialise every polynomial coefficient with two uniform-register
+// moves at the point of use (about 50 issue slots per exp + log pair in the member loop, which is bound by issue slots:
+// an FP64 instruction takes two) and spend about 40 FP64 instructions on the pair.  These take their coefficients from
+// the constant bank and are table-driven (math_tables.cuh: 2^(j/64) for exp, {c, 1/c, log c} on a 1/256 grid for log), so
+// that degree-5 / degree-6 polynomials suffice: 10 + 13 FP64 instructions.  The rare arguments outside the plain
+// range (|x| >= 700; zero, negative, subnormal, infinite or NaN y) go to the library functions.  Error <= 1 ulp against
+// the exact value on the fast paths (tests/test_device_math.py compares both with the host library, which is within an
+// ulp itself, over the ranges the components use).
+// ---------------------------------------------------------------------------
+// {64/ln2, ln2/64 (31 significant bits), its remainder, 1/2, 1/6, 1/24, 1/120}
+__constant__ double RSCM_EXP_C[7] = {92.33248261689366, 0.01083042468962958, 6.619564634077006e-12, 0.5,
+                                     0.16666666666666666, 0.041666666666666664, 0.0083333333333333332};
+// {ln2 (31 significant bits), its remainder, -1/2, 1/3, -1/4, 1/5, -1/6}
+__constant__ double RSCM_LOG_C[7] = {0.6931471801362932, 4.236521365809284e-10, -0.5, 0.33333333333333331, -0.25, 0.20000000000000001,
+                                     -0.16666666666666666};
+
+// the library versions, out of line: they are the rare path and must not bloat the member loop
+__device__ __noinline__ double rscm_exp_slow(double x) { return exp(x); }
+__device__ __noinline__ double rscm_log_slow(double y) { return log(y); }
+
+__device__ __forceinline__ double rscm_exp(double x)
+{
+    const int hx = __double2hiint(x);
+    if ((hx & 0x7fffffff) >= 0x4085e000) return rscm_exp_slow(x); // |x| >= 700, inf, NaN: scaling below would leave the normal range
+    const double magic = 6755399441055744.0;           // 1.5 * 2^52: round to nearest integer in the low word
+    const double t = fma(x, RSCM_EXP_C[0], magic);
+    const int k = __double2loint(t);
+    const double kd = t - magic;
+    double r = fma(kd, -RSCM_EXP_C[1], x);
+    r = fma(kd, -RSCM_EXP_C[2], r);                     // |r| <= ln2/128
+    double q = fma(r, RSCM_EXP_C[6], RSCM_EXP_C[5]);
+    q = fma(r, q, RSCM_EXP_C[4]);
+    q = fma(r, q, RSCM_EXP_C[3]);
+    const double p = fma(r * r, q, r);                  // e^r - 1, truncation r^6/720 < 4e-17
+    const double tj = __ldg(RSCM_EXP_TAB + (k & 63));         // per-lane index: through L1, not the constant bank
+    const double v = fma(tj, p, tj);                    // in [1, 2 (1 + 2^-7))
+    return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+}
+
+// log y = e ln2 + log c + log(1 + u): m = y 2^-e in [sqrt(1/2), sqrt(2)), c = the nearest multiple of 1/256 (m - c is
+// exact), u = (m - c)/c with |u| < 2^-8.5, so that u - u^2/2 + ... - u^6/6 is exact to 2^-54 relative; log c comes as a
+// high and a low part from the table (math_tables.cuh; per-lane indices: global memory through L1, not the constant
+// bank, which would serialise them).  The cell c = 1 has log c = 0 and 1/c = 1: log is exact around 1 and log 1 = 0.
+__device__ __forceinline__ double rscm_log(double y)
+{
+    int hy = __double2hiint(y);
+    if (static_cast<unsigned>(hy - 0x00100000) >= 0x7fe00000u) return rscm_log_slow(y); // zero, negative, subnormal, inf, NaN
+    int e = (hy >> 20) - 1023;
+    hy = (hy & 0x000fffff) | 0x3ff00000;
+    if (hy >= 0x3ff6a09f) { hy -= 0x00100000; e += 1; } // m in [sqrt(1/2), sqrt(2))
+    const double m = __hiloint2double(hy, __double2loint(y));
+    const int j = __double2loint(fma(m, 256.0, 6755399441055744.0)) - RSCM_LOG_J0;
+    const double2 t01 = __ldg(reinterpret_cast<const double2 *>(RSCM_LOG_TAB[j]));
+    const double2 t23 = __ldg(reinterpret_cast<const double2 *>(RSCM_LOG_TAB[j]) + 1);
+    const double u = (m - t01.x) * t01.y;
+    double p = fma(u, RSCM_LOG_C[6], RSCM_LOG_C[5]);
+    p = fma(u, p, RSCM_LOG_C[4]);
+    p = fma(u, p, RSCM_LOG_C[3]);
+    p = fma(u, p, RSCM_LOG_C[2]);
+    const double r = fma(u * u, p, u);
+    const double ed = static_cast<double>(e);
+    return fma(ed, RSCM_LOG_C[0], t23.x + (r + fma(ed, RSCM_LOG_C[1], t23.y)));
+}
+
 template <class R> __device__ __forceinline__ R r_exp(R x);
-template <> __device__ __forceinline__ double r_exp<double>(double x) { return exp(x); }
+template <> __device__ __forceinline__ double r_exp<double>(double x) { return rscm_exp(x); }
 template <> __device__ __forceinline__ float r_exp<float>(float x) { return expf(x); }
 template <class R> __device__ __forceinline__ R r_log(R x);
-template <> __device__ __forceinline__ double r_log<double>(double x) { return log(x); }
+template <> __device__ __forceinline__ double r_log<double>(double x) { return rscm_log(x); }
 template <> __device__ __forceinline__ float r_log<float>(float x) { return logf(x); }
 template <class R> __device__ __forceinline__ R r_sqrt(R x);
 template <> __device__ __forceinline__ double r_sqrt<double>(double x) { return sqrt(x); }
@@ -61,7 +127,7 @@ template <> __device__ __forceinline__ float r_nan<float>() { return __int_as_fl
 // ---------------------------------------------------------------------------
 // TwoLayer — crates/rscm-two-layer/src/component.rs
 //   P: lambda0, a, efficacy, eta, heat_capacity_surface, heat_capacity_deep
-//   D: h k1, h k2, h k3 (below), h/Cs, h eta/Cd   (h = 0.1, the fixed RK4 step)
+//   D: (h/6) k1, (h/6) k2, (h/6) k3 (below), (h/6)/Cs, (h/6) eta/Cd   (h = 0.1, the fixed RK4 step)
 //   in : erf (get()), Ts (at_start), Td (at_start)      out: Ts, Td
 // RK4 (ode_solvers 0.6.1 as called from rscm-core/src/ivp/mod.rs:245-253):
 // nsub fixed steps of h = 0.1 (component.rs:240); the third state (cumulative
@@ -76,25 +142,27 @@ constexpr int TWO_LAYER_ND = 5;
 // is evaluated in the expanded form  F/Cs + Ts (k1 + k3 Ts) + k2 Td  with
 //   k1 = -(lambda0 + x)/Cs, k2 = x/Cs, k3 = a/Cs      (3 FMAs per evaluation)
 // and dTd = (Ts - Td) * (eta/Cd).  Same polynomial, different association: O(1 ulp).
-// The fixed RK4 step h = 0.1 (component.rs:238-243) is folded into the coefficients, so a right-hand side returns
-// h*f: the stage points are y + K/2 and y + K (weights that are instruction immediates) and only 1/6 stays a constant.
+// The fixed RK4 step h = 0.1 (component.rs:238-243) is folded into the coefficients as h/6 (two_layer_prepare).
 template <class R>
 __device__ __forceinline__ void two_layer_prepare(const R *P, R *D)
 {
-    const R h = R(0.1);
+    // h/6 is folded in: a right-hand side returns (h/6) f, the RK4 stage points are y + 3 K, y + 3 K, y + 6 K and the
+    // update is y + (K0 + 2 K1 + 2 K2 + K3) — every weight is an instruction immediate (1/6 is not: it would be
+    // re-materialised with two moves wherever it is used)
+    const R h6 = R(0.1) / R(6);
     const R x = P[2] * P[3];
     const R inv_cs = R(1) / P[4];
-    D[0] = -(P[0] + x) * inv_cs * h;
-    D[1] = x * inv_cs * h;
-    D[2] = P[1] * inv_cs * h;
-    D[3] = inv_cs * h;
-    D[4] = P[3] / P[5] * h;
+    D[0] = -(P[0] + x) * inv_cs * h6;
+    D[1] = x * inv_cs * h6;
+    D[2] = P[1] * inv_cs * h6;
+    D[3] = inv_cs * h6;
+    D[4] = P[3] / P[5] * h6;
 }
 
 template <class R>
 __device__ __forceinline__ void two_layer_rhs(R k0, R k1, R k2, R k3, R eta_cd, R ts, R td, R &dts, R &dtd)
 {
-    // calculate_dy_dt — component.rs:160-188 (times h)
+    // calculate_dy_dt — component.rs:160-188 (times h/6)
     dts = ts * (k3 * ts + k1) + (td * k2 + k0);
     dtd = (ts - td) * eta_cd;
 }
@@ -104,11 +172,11 @@ __device__ __forceinline__ void two_layer_rk4_step(R k0, R k1, R k2, R k3, R eta
 {
     R a0, b0, a1, b1, a2, b2, a3, b3;
     two_layer_rhs(k0, k1, k2, k3, eta_cd, ts, td, a0, b0);
-    two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a0 * R(0.5), td + b0 * R(0.5), a1, b1);
-    two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a1 * R(0.5), td + b1 * R(0.5), a2, b2);
-    two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a2, td + b2, a3, b3);
-    ts = ts + (a0 + a1 * R(2) + a2 * R(2) + a3) * R(1.0 / 6.0);
-    td = td + (b0 + b1 * R(2) + b2 * R(2) + b3) * R(1.0 / 6.0);
+    two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a0 * R(3), td + b0 * R(3), a1, b1);
+    two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a1 * R(3), td + b1 * R(3), a2, b2);
+    two_layer_rhs(k0, k1, k2, k3, eta_cd, ts + a2 * R(6), td + b2 * R(6), a3, b3);
+    ts = ts + ((a0 + a1 * R(2)) + (a2 * R(2) + a3));
+    td = td + ((b0 + b1 * R(2)) + (b2 * R(2) + b3));
 }
 
 template <class R>
@@ -117,7 +185,7 @@ __device__ __forceinline__ bool two_layer_solve(const R *, const R *D, const R *
     const int nsub = cx.nsub[nr.rk * cx.Tpad + cx.N];
     if (nsub < 0) return false; // get_last_step assertion (ivp/mod.rs:94-97) would fire
     const R k1 = D[0], k2 = D[1], k3 = D[2], eta_cd = D[4];
-    const R k0 = in[0] * D[3]; // h F / Cs, F frozen over the step
+    const R k0 = in[0] * D[3]; // (h/6) F / Cs, F frozen over the step
     R ts = in[1], td = in[2];
     if (nsub == 10) { // annual steps: straight-line code (block-uniform branch)
 #pragma unroll

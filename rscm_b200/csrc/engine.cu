@@ -975,6 +975,17 @@ int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops)
     return RSCM_B200_OK;
 }
 
+int rscm_b200_device_math(int op, const double *d_x, int64_t n, double *d_y, void *stream)
+{
+    rscm_b200_ensemble *h = nullptr;
+    if ((op != 0 && op != 1) || !d_x || !d_y || n < 0) return fail(nullptr, RSCM_B200_EINVAL, "device_math: bad argument");
+    if (n == 0) return RSCM_B200_OK;
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+    rscm_dev::device_math_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(op, d_x, n, d_y);
+    CU(cudaGetLastError());
+    return RSCM_B200_OK;
+}
+
 // ---- stretch move (sampler/moves.rs, sampler/ensemble.rs:489-546) -------------------------------------------------
 int rscm_b200_stretch_propose(const double *d_positions, int64_t ld, int n_cols, int64_t active_begin, int64_t n_active,
                               int64_t comp_begin, int64_t n_comp, double a, uint64_t seed, uint32_t step, double *d_proposals,

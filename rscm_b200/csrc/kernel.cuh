@@ -532,6 +532,13 @@ __global__ void pack_scenarios_kernel(const double *__restrict__ src, double *__
 
 // params transpose [M][n_cols] -> [n_cols][M] is not needed: the kernel takes strides.
 
+// self-test hook for the device exp / log (components.cuh): y[i] = f(x[i])
+__global__ void device_math_kernel(int op, const double *__restrict__ x, long long n, double *__restrict__ y)
+{
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        y[i] = op == 0 ? rscm_exp(x[i]) : rscm_log(x[i]);
+}
+
 // FMA-pipe saturating micro-benchmark (roofline denominator for the FP64/FP32 bound)
 template <class R>
 __global__ void __launch_bounds__(256) fma_peak_kernel(R *sink, int iters, R seed)
