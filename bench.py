@@ -240,7 +240,7 @@ def sources_sha16() -> str:
     """Hash of the device sources the headline kernel is built from: keys profiles/traffic.json to the code it measured."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("kernel.cuh", "components.cuh"):
+    for f in ("kernel.cuh", "components.cuh", "math_tables.cuh"):
         h.update(open(os.path.join(ROOT, "rscm_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 

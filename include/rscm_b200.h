@@ -312,6 +312,17 @@ double rscm_b200_kernel_ms(rscm_b200_ensemble *h, int reset);
  * throughput of `device` in TFLOP/s (2 flop per FMA) */
 int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops);
 
+/* ---- scenario ingestion on the device -----------------------------------------
+ * Timeseries::interpolate_into (crates/rscm-core/src/timeseries.rs:586-611; the step ModelBuilder::build applies to every
+ * exogenous series, model/builder.rs:768) for n_series series that share one source axis: source values
+ * [n_series][K][R] at times d_src_times[K] (time_axis.values()), result [n_series][T][R] at d_dst_times[T].
+ * strategy 0 = Linear (interpolate/strategies/linear_spline.rs:33-95), 1 = Next, 2 = Previous, with the is_close!
+ * boundary snap (strategies/mod.rs:38-41) and extrapolation beyond both ends, as interpolate_into allows.  With
+ * n_series = S * n_exogenous this turns scenario files of any resolution into the [S][n_exo][T][R] block
+ * rscm_b200_run_device takes, without a host pass.  Device pointers; asynchronous on `stream`. */
+int rscm_b200_interpolate_device(const double *d_src_times, int64_t K, const double *d_src_values, int64_t n_series, int R,
+                                 const double *d_dst_times, int64_t T, int strategy, double *d_out, void *stream);
+
 /* Self-test hook: y[i] = exp(x[i]) (op 0) or log(x[i]) (op 1) with the engine's own fp64 device implementations
  * (constant-bank coefficients; rscm_b200/csrc/components.cuh), so that their accuracy can be checked from the host. */
 int rscm_b200_device_math(int op, const double *d_x, int64_t n, double *d_y, void *stream);

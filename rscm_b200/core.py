@@ -159,6 +159,37 @@ def _interp(strategy: InterpolationStrategy, time: np.ndarray, y: np.ndarray, ta
     return float(y[e])
 
 
+_STRATEGY_ABI = {InterpolationStrategy.Linear: 0, InterpolationStrategy.Next: 1, InterpolationStrategy.Previous: 2}
+
+
+def interpolate_device(src_times, src_values, dst_times, strategy: InterpolationStrategy = InterpolationStrategy.Linear, out=None,
+                       stream: int = 0):
+    """``Timeseries::interpolate_into`` for a batch of series on the GPU (``rscm_b200_interpolate_device``).
+
+    ``src_times`` [K] and ``dst_times`` [T] are axis VALUES (timeseries.rs:586-611); ``src_values`` is a CUDA tensor
+    [..., K] or [..., K, R] (R = 2 or 4 for grid series).  Returns a CUDA tensor [..., T] / [..., T, R]; results equal the
+    host ``interpolate_into`` bit for bit.  Host arrays are uploaded; the values themselves never visit the host."""
+    import torch
+
+    def dev(x):
+        return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+    st, dt, sv = dev(src_times), dev(dst_times), dev(src_values).contiguous()
+    K, T = st.numel(), dt.numel()
+    if sv.shape[-1] == K:
+        R, lead = 1, tuple(sv.shape[:-1])
+    elif sv.dim() >= 2 and sv.shape[-2] == K and sv.shape[-1] in (2, 4):
+        R, lead = sv.shape[-1], tuple(sv.shape[:-2])
+    else:
+        raise ValueError(f"src_values {tuple(sv.shape)} does not end in [K={K}] or [K, R]")
+    n_series = int(np.prod(lead)) if lead else 1
+    shape = lead + ((T,) if R == 1 else (T, R))
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float64, device=sv.device)
+    _ffi.check(_ffi.lib.rscm_b200_interpolate_device(st.data_ptr(), K, sv.data_ptr(), n_series, R, dt.data_ptr(), T, _STRATEGY_ABI[strategy],
+                                                     out.data_ptr(), stream))
+    return out
+
+
 class _GridTimeseries:
     """GridTimeseries<T, G> — values [T][R], NaN-initialised, `latest` tracking
     (crates/rscm-core/src/timeseries.rs:261-275, 334-345, 387-397)."""

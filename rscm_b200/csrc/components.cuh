@@ -34,6 +34,7 @@ template <class R> struct StepCtx {
     int Tpad;
     int N;                // current time index
     int role;             // lane of this thread within its member's lane group (0 when Prog::LANES == 1)
+    int lanes;            // Prog::LANES
     unsigned mask;        // the warp's lanes that step (shuffle mask for lane groups)
 };
 

@@ -975,6 +975,21 @@ int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops)
     return RSCM_B200_OK;
 }
 
+int rscm_b200_interpolate_device(const double *d_src_times, int64_t K, const double *d_src_values, int64_t n_series, int R,
+                                 const double *d_dst_times, int64_t T, int strategy, double *d_out, void *stream)
+{
+    rscm_b200_ensemble *h = nullptr;
+    if (!d_src_times || !d_src_values || !d_dst_times || !d_out) return fail(nullptr, RSCM_B200_EINVAL, "interpolate: null argument");
+    if (K < 2 || T < 1 || n_series < 1 || (R != 1 && R != 2 && R != 4)) return fail(nullptr, RSCM_B200_EINVAL, "interpolate: need at least 2 source times, 1, 2 or 4 regions");
+    if (strategy < 0 || strategy > 2) return fail(nullptr, RSCM_B200_EINVAL, "interpolate: strategy is 0 (Linear), 1 (Next) or 2 (Previous)");
+    const long long total = n_series * T;
+    const unsigned blocks = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148 * 16));
+    rscm_dev::interpolate_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_src_times, K, d_src_values, n_series, R, d_dst_times, T,
+                                                                                      strategy, d_out);
+    CU(cudaGetLastError());
+    return RSCM_B200_OK;
+}
+
 int rscm_b200_device_math(int op, const double *d_x, int64_t n, double *d_y, void *stream)
 {
     rscm_b200_ensemble *h = nullptr;

@@ -137,10 +137,11 @@ static std::vector<double> ocean_irf_table(const std::vector<double> &p, int n_t
     const int steps = static_cast<int>(p[10]);
     if (steps < 1 || steps > 16 || p[10] != steps) { err = "OceanCarbon: steps_per_year must be an integer in [1, 16]"; return {}; }
     const long long months = static_cast<long long>(steps) * (n_times - 1);
-    if (months > static_cast<long long>(p[11])) {
-        err = "OceanCarbon: run length exceeds max_history_months (history truncation is not implemented on the device)";
-        return {};
-    }
+    // flux_history is a deque bounded by max_history_months (ocean.rs:224-228): a flux older than that has left the
+    // convolution.  The table states this as zero weights from lag max_history_months on (and carries a zero margin for
+    // the sliding windows the device code loads).
+    const double max_hist = p[11];
+    if (!(max_hist >= 1.0)) { err = "OceanCarbon: max_history_months must be at least 1"; return {}; }
     auto form = [](const double *f, double t) {
         const int n = static_cast<int>(f[1]);
         if (f[0] == 0.0) {
@@ -153,8 +154,9 @@ static std::vector<double> ocean_irf_table(const std::vector<double> &p, int n_t
         return s;
     };
     if (p[14] < 1 || p[14] > 8 || p[32] < 1 || p[32] > 8) { err = "OceanCarbon: IRF forms take 1..8 terms"; return {}; }
-    std::vector<double> tab(static_cast<size_t>(months) + 2);
-    for (size_t k = 0; k < tab.size(); ++k) {
+    std::vector<double> tab(static_cast<size_t>(months) + 2 + 96, 0.0);
+    for (size_t k = 0; k < static_cast<size_t>(months) + 2; ++k) {
+        if (static_cast<double>(k) >= max_hist) break; // lag k means k + 1 entries of history
         const double t = static_cast<double>(k) * (1.0 / 12.0);
         const double raw = (t < p[12]) ? form(&p[13], t) : form(&p[31], t);
         tab[k] = (raw * p[6]) / (raw * p[6] + 1.0 - raw);
@@ -409,7 +411,9 @@ static const std::vector<KindInfo> &kinds()
          {0, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 0, 0,
           0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
           1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0},
-         48, /*n_state*/ 1, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10},
+         48, /*n_state*/ 1, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10,
+         /*scratch_fixed*/ 0, /*no_slots*/ false, /*lanes*/ 1, /*aux_template*/ false,
+         /*n_smem_lanes: block-prefix sums of the convolution, one year per lane of a quad*/ 16},
     };
     static const bool extended = (k.push_back(halocarbon_kind()), true);
     (void)extended;
@@ -532,6 +536,7 @@ static void emit_program(Graph &g)
     o << "    static constexpr int NS = " << g.n_state << ";\n";
     o << "    static constexpr int NSM = " << g.n_smem << ";\n";
     o << "    static constexpr int LANES = " << g.lanes << ";\n";
+    o << "    static constexpr bool SYNC_STEPS = " << (g.n_cells > 64 ? "true" : "false") << ";\n";
     o << "    static constexpr bool NEEDS_TIME = " << (g.needs_time ? "true" : "false") << ";\n";
     // exogenous rows are staged into shared memory unless per-thread scratch or a long row list needs the space
     g.stage_exo = (g.n_smem == 0 || g.lanes > 1) && g.n_exo_rows <= 24;
@@ -934,6 +939,10 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         // reads NaN at N+1 just as it does in the reference (no topological re-sort).
     }
 
+    // lanes per member of the program = the largest of its kinds (decides which kinds get lane-group scratch below)
+    for (const Node &n : g.nodes)
+        if (n.kind != KIND_AGGREGATOR) g.lanes = std::max(g.lanes, kind_info(n.kind)->lanes);
+
     // parameter / derived slots, RK4 tables
     for (size_t ni = 0; ni < g.nodes.size(); ++ni) {
         Node &n = g.nodes[ni];
@@ -955,8 +964,7 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         n.scratch_base = g.n_scratch_rows;
         n.ctab_base = static_cast<int>(g.ctab.size());
         g.n_state += k->n_state;
-        g.n_smem += k->n_smem;
-        g.lanes = std::max(g.lanes, k->lanes);
+        g.n_smem += k->n_smem + (g.lanes > 1 ? k->n_smem_lanes : 0);
         g.n_scratch_rows += k->scratch_fixed + k->scratch_per_T * g.T;
         g.needs_time = g.needs_time || k->needs_time;
         if (k->const_table) {
@@ -964,6 +972,16 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
             const std::vector<double> tab = k->const_table(n.params, terr);
             if (!terr.empty()) { err = terr; return false; }
             g.ctab.insert(g.ctab.end(), tab.begin(), tab.end());
+            if (n.kind == RSCM_B200_HALOCARBON_CHEMISTRY) {
+                // decay factors exp(-dt / lifetime) per species (halocarbon.rs:115-134) for the step length of a uniform
+                // time axis: {dt_ref (NaN when the steps differ), 41 factors}.  Lifetimes are per-graph, so on a uniform
+                // axis the 41 exponentials per member-year are constants of the graph.
+                double dt_ref = g.bounds[1] - g.bounds[0];
+                for (int t = 1; t < g.T; ++t)
+                    if (g.bounds[t + 1] - g.bounds[t] != dt_ref) dt_ref = std::nan("");
+                g.ctab.push_back(dt_ref);
+                for (int sp = 0; sp < kHaloNS; ++sp) g.ctab.push_back(std::exp(-dt_ref / tab[6 * sp]));
+            }
         }
         n.gtab_base = static_cast<int>(g.gtab.size());
         if (k->global_table) {

@@ -53,6 +53,7 @@ struct KindInfo {
     bool no_slots = false; // all parameters are per-graph and only feed const_table: they take no kernel parameter slots
     int lanes = 1; // lanes of a warp that work on one member (ClimateUDEB: 4); the program takes the largest of its kinds
     bool aux_template = false; // the aux literal is also a template argument of <dev_name>_solve / _init_state
+    int n_smem_lanes = 0; // extra per-thread shared-memory words when the PROGRAM runs lane groups (Prog::LANES > 1)
 };
 
 const KindInfo *kind_info(int kind);

@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     cx.Tpad = a.Tpad;
     cx.N = 0;
     cx.role = role;
+    cx.lanes = LANES;
     cx.mask = step_mask;
     R S[Prog::NS > 0 ? Prog::NS : 1];
     if (!LOGP || active) Prog::template init_state<R>(P, D, S, cx);
@@ -341,6 +342,10 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
 
     const int T = a.T;
     for (int N = 0; N < T - 1; ++N) {
+        // Programs whose step is far larger than the instruction cache (the 124-variable MAGICC chain: 128 KB of SASS per
+        // model year) keep the warps of a CTA in step, so that they fetch the same instructions together instead of
+        // streaming four copies.  (Padding threads have exited or skip the step; a barrier counts non-exited threads.)
+        if (Prog::SYNC_STEPS) __syncthreads();
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(x_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
@@ -531,6 +536,64 @@ __global__ void pack_scenarios_kernel(const double *__restrict__ src, double *__
 }
 
 // params transpose [M][n_cols] -> [n_cols][M] is not needed: the kernel takes strides.
+
+// Timeseries::interpolate_into on the device (crates/rscm-core/src/timeseries.rs:586-611 -> Interp1d over the axis VALUES;
+// strategies interpolate/strategies/{linear_spline,previous,next}.rs, segment search strategies/mod.rs:24-68 with the
+// is_close! boundary snap, relative tolerance 1e-8).  One thread per (series, target time); extrapolation allowed, as in
+// interpolate_into.  strategy: 0 Linear (the last source time is trimmed before the search; beyond the ends the first /
+// last segment is extended), 1 Next, 2 Previous.  src [n_series][K][R], dst [n_series][T][R].
+__device__ __forceinline__ bool interp_is_close(double a, double b)
+{
+    return fabs(a - b) <= 1e-8 * fmax(fabs(a), fabs(b));
+}
+
+__global__ void interpolate_kernel(const double *__restrict__ src_t, long long K, const double *__restrict__ src_v, long long n_series, int R,
+                                   const double *__restrict__ dst_t, long long T, int strategy, double *__restrict__ dst_v)
+{
+    const long long total = n_series * T;
+    for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total; g += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long s = g / T, i = g % T;
+        const double target = dst_t[i];
+        const long long nb = strategy == 0 ? K - 1 : K; // searched boundaries
+        long long lo = 0, hi = nb;                      // lower bound: first index with src_t[idx] >= target
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (src_t[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        const long long idx = lo;
+        const bool fwd = idx == nb, bwd = !fwd && idx == 0;
+        const bool boundary = !fwd && interp_is_close(src_t[idx], target);
+        const double *y = src_v + s * K * R;
+        double *out = dst_v + (s * T + i) * R;
+        for (int r = 0; r < R; ++r) {
+            double v;
+            if (strategy == 0) {
+                const long long e = idx < K - 1 ? idx : K - 1;
+                if (boundary) v = y[e * R + r];
+                else {
+                    long long i1, i2;
+                    if (bwd) { i1 = 0; i2 = 1; }
+                    else if (fwd) { i1 = K - 2; i2 = K - 1; }
+                    else { i1 = e - 1; i2 = e; }
+                    const double t1 = src_t[i1], t2 = src_t[i2], y1 = y[i1 * R + r], y2 = y[i2 * R + r];
+                    const double m = __ddiv_rn(y2 - y1, t2 - t1);
+                    v = __dadd_rn(__dmul_rn(m, target - t1), y1); // m * (target - t1) + y1, not contracted (host arithmetic)
+                }
+            } else if (strategy == 2) { // Previous
+                if (boundary) v = y[idx * R + r];
+                else if (bwd) v = y[r];
+                else if (fwd) v = y[(K - 1) * R + r];
+                else v = y[(idx - 1) * R + r];
+            } else { // Next
+                const long long e = idx < K - 1 ? idx : K - 1;
+                if (bwd) v = y[r];
+                else if (fwd) v = y[(K - 1) * R + r];
+                else v = y[e * R + r];
+            }
+            out[r] = v;
+        }
+    }
+}
 
 // self-test hook for the device exp / log (components.cuh): y[i] = f(x[i])
 __global__ void device_math_kernel(int op, const double *__restrict__ x, long long n, double *__restrict__ y)

@@ -182,10 +182,17 @@ __device__ __forceinline__ bool n2o_chemistry_solve(const R *P, const R *, const
 // ---- OceanCarbon — carbon/ocean.rs:167-260: monthly air-sea flux + impulse-response convolution --------------------
 // The reference re-sums the whole monthly flux history against the (nonlinearly scaled) IRF every month:
 // O((12 T)^2 / 2) multiply-adds per run.  Here the scaled IRF is a per-graph table (cx.gtab, lag in months; the IRF
-// parameters are per-graph), the flux history lives in the member-interleaved global scratch, and the history that
-// predates the current year is read ONCE per year while the partial sums of all `steps` months of the year are
-// advanced together (steps FMAs per load) — in the reference's oldest-to-newest order, so the sums are the same
-// up to FMA contraction.  P: see include/rscm_b200.h (60 values); S[0] = months of history so far.
+// parameters are per-graph; zero from lag max_history_months on: the reference's bounded deque), the flux history lives
+// in the member-interleaved global scratch, and the partial sums of all `steps` months of a year are advanced together
+// (steps FMAs per load) in the reference's oldest-to-newest order, so the sums are the same up to FMA contraction.
+//   * one thread per member (Prog::LANES == 1): the history that predates the current year is read once per year;
+//   * lane quads (a program with ClimateUDEB): years are taken in blocks of four.  At the first year of a block lane q
+//     sums the whole history that predates the block against the lags of the block's year q (12 prefix sums, kept in
+//     this lane's shared-memory column); every year then starts from the prefix sums of its lane and adds the block's
+//     own months.  The long history is read once per FOUR years and by four lanes at once (it is the HBM traffic
+//     that bounds the emissions-driven chain: 4200 months x 8 B per member at the end of a 350-year run), the
+//     accumulation order per month is unchanged (history before the block, then the block, oldest first).
+// P: see include/rscm_b200.h (60 values); S[0] = months of history so far.
 template <class R> __device__ __forceinline__ void ocean_carbon_prepare(const R *P, R *D)
 {
     D[0] = P[3] / (P[4] * R(12));            // gas_exchange_rate
@@ -207,34 +214,60 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     const double *irf = cx.gtab + nr.gt;
     double *hist = cx.scratch + static_cast<long long>(nr.scr) * cx.runs;
     R acc[MAXS];
+    // sum over history entries [i0, i1) against the lags of months `first_month + m` (m < steps), oldest entry first.
+    // Chunks of 16 months: sixteen independent (coalesced, member-interleaved) flux loads in flight, and the IRF lags of a
+    // chunk form one sliding window of 15 + steps values (uniform loads) instead of steps loads per month.
+    auto convolve = [&](int i0, int i1, int first_month) {
+        constexpr int CH = 16;
+        int i = i0;
+        for (; i + CH <= i1; i += CH) {
+            R f[CH];
 #pragma unroll
-    for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
-    // History in chunks of 16 months: sixteen independent (coalesced, member-interleaved) flux loads in flight instead of
-    // one per iteration, and the IRF lags of a chunk form one sliding window of 15 + steps values (uniform loads) instead
-    // of steps loads per month.  Same accumulation order (oldest flux first) as the month-by-month loop.
-    constexpr int CH = 16;
-    int i = 0;
-    for (; i + CH <= n_old; i += CH) {
-        R f[CH];
+            for (int u = 0; u < CH; ++u) f[u] = R(hist[static_cast<long long>(i + u) * cx.runs]);
+            const double *wb = irf + (first_month - i - (CH - 1)); // wb[k]: lag first_month - i - (CH - 1) + k
+            R wv[CH - 1 + MAXS];
 #pragma unroll
-        for (int u = 0; u < CH; ++u) f[u] = R(hist[static_cast<long long>(i + u) * cx.runs]);
-        const double *wb = irf + (n_old - i - (CH - 1)); // wb[k]: lag n_old - i - (CH - 1) + k
-        R wv[CH - 1 + MAXS];
+            for (int k = 0; k < CH - 1 + MAXS; ++k)
+                if (k < CH - 1 + steps) wv[k] = R(__ldg(wb + k));
 #pragma unroll
-        for (int k = 0; k < CH - 1 + MAXS; ++k)
-            if (k < CH - 1 + steps) wv[k] = R(__ldg(wb + k));
+            for (int u = 0; u < CH; ++u)
 #pragma unroll
-        for (int u = 0; u < CH; ++u)
+                for (int m = 0; m < MAXS; ++m)
+                    if (m < steps) acc[m] += f[u] * wv[(CH - 1 - u) + m];
+        }
+        for (; i < i1; ++i) {
+            const R f = R(hist[static_cast<long long>(i) * cx.runs]);
+            const double *w = irf + (first_month - i);
 #pragma unroll
             for (int m = 0; m < MAXS; ++m)
-                if (m < steps) acc[m] += f[u] * wv[(CH - 1 - u) + m];
-    }
-    for (; i < n_old; ++i) {
-        const R f = R(hist[static_cast<long long>(i) * cx.runs]);
-        const double *w = irf + (n_old - i);
+                if (m < steps) acc[m] += f * R(__ldg(w + m));
+        }
+    };
+    // a flux older than max_history_months has left the reference's deque: no need to load it (its weights are zero)
+    const int max_hist = static_cast<int>(P[11]);
+    if (cx.lanes == 4) {
+        R *A = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R))); // this lane's prefix sums, month m at A[m * BLOCK]
+        const int yb = (n_old / steps) & 3;                               // year within the block of four
+        if (yb == 0) {
+            const int first_month = n_old + steps * cx.role;              // lane q prepares year q of the block
 #pragma unroll
-        for (int m = 0; m < MAXS; ++m)
-            if (m < steps) acc[m] += f * R(__ldg(w + m));
+            for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
+            const int lo = first_month + 1 - max_hist;
+            convolve(lo > 0 ? (lo < n_old ? lo : n_old) : 0, n_old, first_month);
+#pragma unroll
+            for (int m = 0; m < MAXS; ++m)
+                if (m < steps) A[m * BLOCK] = acc[m];
+            __syncwarp(cx.mask);
+        }
+        const R *Ay = A + (yb - cx.role); // the column of the lane that prepared this year (same quad, same warp)
+#pragma unroll
+        for (int m = 0; m < MAXS; ++m) acc[m] = (m < steps) ? Ay[m * BLOCK] : R(0);
+        convolve(n_old - yb * steps, n_old, n_old); // the block's own months so far (just written: L1 / L2 resident)
+    } else {
+#pragma unroll
+        for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
+        const int lo = n_old + 1 - max_hist;
+        convolve(lo > 0 ? (lo < n_old ? lo : n_old) : 0, n_old, n_old);
     }
     R fy[MAXS];
     R total_flux = R(0);
@@ -243,7 +276,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     for (int m = 0; m < MAXS; ++m) {
         if (m < steps) {
             const R flux_ppm = k_gas * (co2 - pco2);
-            hist[static_cast<long long>(n_old + m) * cx.runs] = static_cast<double>(flux_ppm);
+            if (cx.role == 0) hist[static_cast<long long>(n_old + m) * cx.runs] = static_cast<double>(flux_ppm);
             fy[m] = flux_ppm;
             const R flux_gtc_yr = flux_ppm * R(12) * R(2.124);
             total_flux += flux_gtc_yr / R(steps);
@@ -261,6 +294,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
             pco2 = (P[2] + dp) * tfac;
         }
     }
+    if (cx.lanes > 1) __syncwarp(cx.mask); // the other lanes of the quad read these months next year
     S[0] = R(n_old + steps);
     out[0] = total_flux;
     out[1] = pco2;
@@ -295,6 +329,8 @@ __device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R 
     const double *tab = cx.ctab + nr.ctab;
     const R dt = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
     R total = R(0), fgas = R(0), montreal = R(0), eesc = R(0);
+    // on a uniform time axis the decay factors are constants of the graph (host-computed, graph.cpp)
+    const bool uniform_dt = static_cast<double>(dt) == tab[HALO_CT * HALO_NS];
 #pragma unroll
     for (int s = 0; s < HALO_NS; ++s) {
         const double *t = tab + HALO_CT * s;
@@ -302,7 +338,7 @@ __device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R 
         R conc = in[2 * s + 1];
         if (conc != conc) conc = S[s]; // latest_value: fall back to the last non-NaN value (NaN if there never was one)
         S[s] = conc;
-        const R decay = r_exp<R>(-dt / lifetime);
+        const R decay = uniform_dt ? R(tab[HALO_CT * HALO_NS + 1 + s]) : r_exp<R>(-dt / lifetime); // block-uniform choice
         const R emissions_ppt = in[2 * s] * conv;
         const R new_conc = conc * decay + emissions_ppt * lifetime * (R(1) - decay);
         out[s] = new_conc;

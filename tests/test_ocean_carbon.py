@@ -62,13 +62,19 @@ def test_equilibrium_stays_at_rest():
     assert np.all(r["Carbon Flux|Ocean"][1:] == 0.0) and np.all(r["Ocean Surface pCO2"] == 278.0)
 
 
-def test_history_limit_is_refused_by_the_engine():
-    from rscm_b200 import _ffi
-    b = (ModelBuilder().with_time_axis(syn.time_axis(1850, 2100))
-         .with_rust_component(OceanCarbonBuilder.from_parameters({"max_history_months": 120}).build())
-         .with_initial_values({"Ocean Surface pCO2": 278.0, "Cumulative Ocean Uptake": 0.0}))
-    with pytest.raises(_ffi.EngineError, match="max_history_months"):
-        b.build_ensemble(device=-2)
+def test_history_limit_truncates_on_the_oracle():
+    """OceanCarbonState::flux_history is a deque bounded by max_history_months (ocean.rs:224-228): once it is full the
+    oldest flux leaves the convolution.  With a 10-year bound the run differs from the unbounded one exactly from the year
+    the bound starts to bite."""
+    def run(max_hist):
+        b = (ModelBuilder().with_time_axis(syn.time_axis(1850, 1900))
+             .with_rust_component(OceanCarbonBuilder.from_parameters({"max_history_months": max_hist}).build())
+             .with_initial_values({"Ocean Surface pCO2": 278.0, "Cumulative Ocean Uptake": 0.0}))
+        sc = {"Atmospheric Concentration|CO2": 278.0 + 2.0 * np.arange(51.0), "Sea Surface Temperature": 0.01 * np.arange(51.0)}
+        return oracle_from_builder(b, sc).run()["Ocean Surface pCO2"]
+    full, cut = run(6000), run(120)
+    assert np.array_equal(full[:11], cut[:11]) and not np.array_equal(full[11:], cut[11:])   # 120 months = 10 years
+    assert np.all(np.isfinite(cut))
 
 
 # ---- GPU parity ---------------------------------------------------------------------------------------------------
@@ -179,3 +185,46 @@ def test_full_magicc_gpu_parity(tmp_path, monkeypatch):
     for n in names:
         assert rel_err(got[n], ref[n]) <= 1e-9, n
     assert np.isfinite(got["Surface Temperature"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_hist", [120, 30, 7])
+def test_ocean_carbon_history_truncation_gpu_parity(max_hist, tmp_path, monkeypatch):
+    """History truncation on the device (zero IRF weights from lag max_history_months on, older fluxes not loaded) against
+    the oracle's bounded history, for bounds above and below one year of months."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    b = (ModelBuilder().with_time_axis(syn.time_axis(1850, 1930))
+         .with_rust_component(OceanCarbonBuilder.from_parameters({"max_history_months": max_hist}).build())
+         .with_initial_values({"Ocean Surface pCO2": 278.0, "Cumulative Ocean Uptake": 0.0}))
+    ens = b.build_ensemble().bind_parameters(OCEAN_BINDS)
+    years = np.arange(81.0)
+    sc = ens.pack_scenarios([{"Atmospheric Concentration|CO2": 278.0 + 1.5 * years + 0.01 * years ** 2, "Sea Surface Temperature": 0.012 * years}])
+    p = syn.uniform_params({"tau": (6.0, 10.0), "sst_pi": (17.0, 19.0), "ts": (0.03, 0.045), "mld": (45.0, 80.0)}, 40, 33)
+    got = ens.split_outputs(ens.run(p, sc))
+    m = oracle_from_builder(b)
+    names = ens.variable_names
+    ref = m.split(m.run_batch(oracle_bindings(b, OCEAN_BINDS), p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
+
+
+@pytest.mark.gpu
+def test_full_magicc_truncated_history_in_lane_quads(tmp_path, monkeypatch):
+    """The emissions-driven chain runs as lane quads (ClimateUDEB): OceanCarbon takes years in blocks of four with the
+    history before the block summed by the four lanes — here with a history bound that cuts inside the blocks."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    from rscm_b200.magicc import OceanCarbonBuilder as OCB
+    b = full_magicc_builder(end=1950)
+    for i, c in enumerate(b._components):
+        if c.type_name == "OceanCarbon":
+            b._components[i] = OCB.from_parameters({"max_history_months": 250}).build()
+    ens = b.build_ensemble().bind_parameters(FULL_BINDS)
+    sc = ens.pack_scenarios([full_magicc_scenario()])
+    p = syn.uniform_params({"ecs": (2.0, 4.5), "beta": (0.4, 0.9), "tau": (6.5, 9.5), "tau_oh": (8.5, 10.5)}, 37, 45)
+    names = ["Atmospheric Concentration|CO2", "Carbon Flux|Ocean", "Ocean Surface pCO2", "Surface Temperature"]
+    ens.select_outputs(names)
+    got = ens.split_outputs(ens.run(p, sc))
+    m = oracle_from_builder(b)
+    ref = m.split(m.run_batch(oracle_bindings(b, FULL_BINDS), p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
