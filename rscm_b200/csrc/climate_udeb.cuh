@@ -6,30 +6,35 @@
 // heat uptake / ocean heat content :262-306), climate/lamcalc.rs (:85-290), climate/state.rs,
 // rscm-core/src/utils/linear_algebra.rs (thomas_solve :41-79, invert_4x4 :102-166).
 //
-// FOUR LANES = ONE MEMBER (Prog::LANES = 4).  The reference solves, twelve times a year and for each hemisphere, a
+// FOUR THREADS = ONE MEMBER (Prog::LANES = 4).  The reference solves, twelve times a year and for each hemisphere, a
 // 50-row tridiagonal system top to bottom: one 50-long recurrence with a division in the loop-carried chain.  Here the
 // system is eliminated from both ends towards the middle (rows 0..k the usual way, rows n-1..k+1 mirrored, a 2x2 solve
 // where they meet, substitution outwards — same solution up to rounding: the matrix is strictly diagonally dominant),
-// and each of the four half-sweeps of a member (2 hemispheres x 2 ends) belongs to one lane of a lane quad:
-//     lane & 1 = hemisphere (0 NH, 1 SH),   lane & 2 = end (0: top sweep, rows 0..k;  2: bottom sweep, rows n-1..k+1).
-// A lane keeps ITS <= 25 rows in registers for the whole run (the temperatures persist in S[], the eliminated
-// super-diagonal lives only inside a sub-step): there is no shared-memory column, no global scratch for the sweep and no
-// address arithmetic; the two ends of a hemisphere exchange three values per sub-step with __shfl_xor (edge temperatures
-// before the sweep, the pivot pair where the sweeps meet) and the quad shares the two sea-surface temperatures after it.
-// Everything that is not a row (LAMCALC, forcing, land / ground boxes, upwelling) is computed redundantly by the four
-// lanes — a few hundred instructions against 25 rows x 12 sub-steps — so all lanes hold identical scalar state.
+// and each of the four half-sweeps of a member (2 hemispheres x 2 ends) belongs to one ROLE:
+//     role & 1 = hemisphere (0 NH, 1 SH),   role & 2 = end (0: top sweep, rows 0..k;  2: bottom sweep, rows n-1..k+1).
+// A CTA of four warps serves 32 members: warp w is role w, lane l is member l (StepCtx, components.cuh), so a warp runs
+// ONE role — no selects or divergence between the top and the bottom sweep — and warp 0 alone runs everything that is
+// not a row: the rest of the component graph, the history sum of the ECS feedback and LAMCALC, whose results it
+// publishes; the other warps wait at a barrier meanwhile and cost no issue slots.  A thread keeps ITS <= 25 rows in
+// registers for the whole run (the temperatures persist in S[], the eliminated off-diagonal lives only inside a sub-step):
+// there is no shared-memory column for them and no address arithmetic.  Per sub-step the four roles meet twice through
+// the member's exchange column in shared memory, each time followed by a __syncthreads(): the pivot pair where the
+// sweeps meet, and after the substitution the new edge temperatures (the top roles' are the sea-surface temperatures
+// every role needs for the land boxes; all four are what the next sub-step's sweeps start from).  The small land / ground /
+// upwelling updates of a sub-step are computed by all four roles, so that they hold identical scalar state.
 // Row coefficients that depend only on geometry (area factors, entrainment combinations of the initial profile,
-// relative depth of the diffusivity profile) come from a host-computed table laid out per lane role and row
+// relative depth of the diffusivity profile) come from a host-computed table laid out per role and row
 // (graph.cpp udeb_const_table), read with 128-bit shared-memory loads at immediate offsets.
 //
 // Where the state lives:
-//   * S[0..18]   (registers, identical in the four lanes): LAMCALC result at the member's base ECS, upwelling rates,
+//   * S[0..18]   (registers, identical in the four roles): LAMCALC result at the member's base ECS, upwelling rates,
 //                land / ground temperatures, alpha_eff, inter-hemispheric exchange, history length;
-//   * S[19..43]  (registers): this lane's rows of the ocean column, sweep order (row 0 = the lane's end of the column);
-//   * cx.sm      (shared memory, [25][BLOCK] per CTA, conflict-free): the eliminated off-diagonal of the lane's rows,
+//   * S[19..43]  (registers): this role's rows of the ocean column, sweep order (row 0 = the role's end of the column);
+//   * cx.sm      (shared memory, [25][BLOCK] per CTA, conflict-free): the eliminated off-diagonal of the role's rows,
 //                written by the sweep and read back by the substitution of the same sub-step;
+//   * cx.xch     (shared memory, 28 doubles per member): the exchange column;
 //   * cx.scratch (global, member-interleaved [T][runs]): the T*dt history of the cumulative-temperature feedback, each
-//                lane sums a quarter of the window newest-to-oldest and the quad adds the four partial sums;
+//                role sums a quarter of the window newest-to-oldest and role 0 adds the four partial sums;
 //   * cx.ctab    (shared memory, per graph): the role tables.
 #pragma once
 
@@ -241,7 +246,8 @@ template <class R> __device__ __forceinline__ UdebRow<R> udeb_row(const double *
     return r;
 }
 
-template <class R> __device__ __forceinline__ R udeb_shx(unsigned mask, R v, int x) { return __shfl_xor_sync(mask, v, x); }
+// exchange slots of a member's column (relative to NodeRef::xch), see climate_udeb_solve
+enum { UX_EDGE = 0, UX_MEET = 4, UX_HIST = 14, UX_LAM = 18, UX_OHC = 22, UX_T0 = 26 };
 
 // f64::max(x, lo) / f64::min(x, hi) for a bound that is not NaN (the year set-up replaces a NaN bound by -inf / +inf,
 // which is what the NaN-ignoring f64::max / min make of it): one compare and a select instead of the library fmax / fmin
@@ -279,16 +285,19 @@ __device__ __forceinline__ float udeb_cap(float x, float hi) { return x < hi ? x
 // row loops are straight-line code over register rows: the top sweep owns rows 0..K (NT = K + 1 of them), the bottom
 // sweep rows N-1..K+1 (NB = N - K - 1, one more than NT when N is odd — that row is the only predicated one).
 template <class R, int N>
-__device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, const R *S, const double *tab, bool bottom, int h,
-                                             unsigned mask, R *T, R *F, R forcing)
+__device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, const R *S, const double *tab, int role, double *X, R *T,
+                                             R *F, R forcing)
 {
+    const bool bottom = (role & 2) != 0; // warp-uniform
+    const int h = role & 1;
     constexpr int K = (N - 2) >> 1, NT = K + 1, NB = N - K - 1;
     static_assert(NT >= 1 && NB >= NT && NB - NT <= 1 && NB <= UDEB_MAXR, "row split");
     // F: the eliminated off-diagonal of this lane's rows, row j at F[j * BLOCK] (this thread's shared-memory column:
     // consecutive threads, consecutive words); it lives only inside the sub-step
     // edge temperatures of this hemisphere before the solve: the mixed layer (top lane's row 0) and the bottom layer
+    // (every role published its edge temperature T[0] at the end of the previous sub-step, or at the start of the year)
     const R tedge = T[0];
-    const R tpart = udeb_shx(mask, tedge, 2);
+    const R tpart = R(X[(UX_EDGE + (role ^ 2)) * 32]);
     const R t0 = bottom ? tpart : tedge, tbot = bottom ? tedge : tpart;
     const R w = h ? S[US_W1] : S[US_W0];
     const R dkc = y.dkdt_c * (t0 - tbot), dkcA = dkc * y.cA;
@@ -308,19 +317,18 @@ __device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, c
     {
         const UdebRow<R> c = udeb_row<R>(tab);
         const R k = udeb_floor(c.om * dkc + y.kc, y.kmin);
-        // row 0 of the top sweep: mixed layer (ocean_column.rs:93-150); of the bottom sweep: bottom layer, no diffusion
-        // below (:163-175).  Both are evaluated branch-free and selected (a few dozen instructions per sub-step).
-        const R term_diff = k * y.cM, term_upwell = w * y.dt_mix;
-        const R b_top = R(1) + y.tfb_dt * c.at + term_diff * c.af + term_upwell * y.pi_ratio * c.af;
-        R d_top = t0 + (forcing * y.famp + (h ? S[US_HX1] : S[US_HX0])) * y.dt_cmix * c.at;
-        if (y.lhc) d_top -= y.lhc_c * ((h ? S[US_LAND1] : S[US_LAND0]) - (h ? S[US_GR1] : S[US_GR0])) * c.at;
-        d_top += y.dt_mix * dwv * c.g;
-        const R m = k * y.cA * c.at;
-        const R b_bot = R(1) + m + tul * c.at;
-        const R d_bot = tbot + pt0 * c.at + dwc * c.g;
-        q1 = bottom ? b_bot : b_top;
-        g1 = bottom ? m : (term_diff + term_upwell) * c.af;
-        D1 = bottom ? d_bot : d_top;
+        if (!bottom) { // row 0 of the top sweep: mixed layer (ocean_column.rs:93-150)
+            const R term_diff = k * y.cM, term_upwell = w * y.dt_mix;
+            q1 = R(1) + y.tfb_dt * c.at + term_diff * c.af + term_upwell * y.pi_ratio * c.af;
+            D1 = t0 + (forcing * y.famp + (h ? S[US_HX1] : S[US_HX0])) * y.dt_cmix * c.at;
+            if (y.lhc) D1 -= y.lhc_c * ((h ? S[US_LAND1] : S[US_LAND0]) - (h ? S[US_GR1] : S[US_GR0])) * c.at;
+            D1 += y.dt_mix * dwv * c.g;
+            g1 = (term_diff + term_upwell) * c.af;
+        } else { // row 0 of the bottom sweep: bottom layer, no diffusion below (:163-175)
+            g1 = k * y.cA * c.at;
+            q1 = R(1) + g1 + tul * c.at;
+            D1 = tbot + pt0 * c.at + dwc * c.g;
+        }
         const R r = r_rcp(q1);
         fp = g1 * r;
         dp = D1 * r;
@@ -359,7 +367,10 @@ __device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, c
         if (bottom) row(NB - 1);
     }
     // where the sweeps meet: x_K = d'_K + f_K x_{K+1} (top), x_{K+1} = d"_{K+1} + f"_{K+1} x_K (bottom)
-    const R fq = udeb_shx(mask, fp, 2), dq = udeb_shx(mask, dp, 2);
+    X[(UX_MEET + 2 * role) * 32] = static_cast<double>(fp);
+    X[(UX_MEET + 2 * role + 1) * 32] = static_cast<double>(dp);
+    __syncthreads();
+    const R fq = R(X[(UX_MEET + 2 * (role ^ 2)) * 32]), dq = R(X[(UX_MEET + 2 * (role ^ 2) + 1) * 32]);
     const R f_top = bottom ? fq : fp, d_top = bottom ? dq : dp, d_bot = bottom ? dp : dq;
     const R x_top = (d_top + f_top * d_bot) * r_rcp(R(1) - fp * fq);
     R x = bottom ? dp + fp * x_top : x_top;
@@ -382,35 +393,28 @@ __device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, c
 template <class R, int N>
 __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &cx, R *S, NodeRef nr)
 {
-    // No early return: the four lanes of a member take every shuffle together, and the members of a warp must too.  A
-    // member whose from_parameters failed (LAMCALC did not converge) computes on and reports failure at the end.
+    // No early return: the four roles of a member meet at every barrier, and so must all members of the CTA.  A member
+    // whose from_parameters failed (LAMCALC did not converge) computes on and reports failure at the end.
     const bool ok = S[US_OK] != R(0);
     const int steps_n = static_cast<int>(P[U_STEPS]);
     const int q = cx.role, h = q & 1;
     const bool bottom = (q & 2) != 0;
-    const unsigned mask = cx.mask;
     constexpr int K = (N - 2) >> 1, NT = K + 1, NB = N - K - 1;
     R *T = S + US_T;
     R *F = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R)));
+    double *X = cx.xch + nr.xch * 32; // this member's exchange column, slot j at X[j * 32]
     const double *tab = cx.ctab + nr.ctab + q * (UDEB_MAXR * UDEB_CT);
     const R erf_start = in[0], erf_end = in[1];
-    const int lane = static_cast<int>(threadIdx.x) & 31, quad = lane & ~3;
-    if (__shfl_sync(mask, T[0], quad) == R(0) && in[2] != R(0)) { // warm start from non-zero initial surface temperatures (mod.rs:439-448)
-        if (!bottom) T[0] = h ? in[4] : in[2];
-        S[US_LAND0] = in[3]; S[US_LAND1] = in[5];
-        S[US_GR0] = S[US_LAND0]; S[US_GR1] = S[US_LAND1];
-    }
     const R dt_year = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
     const R steps = R(steps_n);
     const R dt_sub = dt_year / steps;
 
     // adjusted_ecs: sum of T*dt over the last `period` years
     const int nhist = static_cast<int>(S[US_NHIST]);
-    R cum_t = R(0);
     {
-        // Which entries the window covers follows from the time axis alone (shared memory, block-uniform): entries
-        // [first, nhist) count fully, entry first-1 with weight `partial` if the window ends inside it.  Each lane of
-        // the quad sums every fourth entry, newest first, with independent loads; the quad adds the partial sums.
+        // Which entries the window covers follows from the time axis alone: entries [first, nhist) count fully, entry
+        // first-1 with weight `partial` if the window ends inside it.  Each role sums every fourth entry, newest first,
+        // with independent loads; role 0 adds the four partial sums.
         R partial = R(0);
         int first = nhist;
         const double *win = cx.gtab + nr.gt; // host-computed window per step for the graph's period (graph.cpp)
@@ -431,21 +435,37 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
 #pragma unroll 4
         for (int i = nhist - 1 - q; i >= first; i -= UDEB_LANES) sum += R(hist[static_cast<long long>(i) * cx.runs]);
         if (q == 0 && partial > R(0) && first > 0) sum += R(hist[static_cast<long long>(first - 1) * cx.runs]) * partial;
-        sum += udeb_shx(mask, sum, 1);
-        sum += udeb_shx(mask, sum, 2);
-        cum_t = sum;
+        X[(UX_HIST + q) * 32] = static_cast<double>(sum);
+        if (q == 0) X[UX_T0 * 32] = static_cast<double>(T[0]); // the NH mixed-layer temperature (warm-start test below)
     }
-    const R cumt_2x = P[U_ECS] * P[U_FB_PERIOD];
-    const R cumt_factor = (r_abs(cumt_2x) > R(1e-15)) ? R(1) + P[U_FB_CUMT] * (cum_t - cumt_2x) / cumt_2x : R(1);
-    const R erf_mid = (erf_start + erf_end) / R(2);
-    const R q_factor = R(1) + P[U_FB_Q] * (udeb_floor(erf_mid, R(0)) - P[U_RF2X]);
-    const R aecs = P[U_ECS] * cumt_factor * q_factor;
-
-    R lam_o = S[US_LAMO], lam_l = S[US_LAML], co2_eff = S[US_EFF];
-    if (r_abs(aecs - P[U_ECS]) > R(1e-10)) {
-        R lo, ll, ef;
-        if (udeb_lamcalc(P, aecs, lo, ll, ef)) { lam_o = lo; lam_l = ll; co2_eff = ef; }
+    __syncthreads();
+    // Role 0 alone turns the history into this year's feedback parameters (LAMCALC: up to 40 secant iterations) and
+    // publishes them; the other warps wait at the barrier.
+    if (q == 0) {
+        const R cum_t = ((R(X[UX_HIST * 32]) + R(X[(UX_HIST + 1) * 32])) + (R(X[(UX_HIST + 2) * 32]) + R(X[(UX_HIST + 3) * 32])));
+        const R cumt_2x = P[U_ECS] * P[U_FB_PERIOD];
+        const R cumt_factor = (r_abs(cumt_2x) > R(1e-15)) ? R(1) + P[U_FB_CUMT] * (cum_t - cumt_2x) / cumt_2x : R(1);
+        const R erf_mid = (erf_start + erf_end) / R(2);
+        const R q_factor = R(1) + P[U_FB_Q] * (udeb_floor(erf_mid, R(0)) - P[U_RF2X]);
+        const R aecs = P[U_ECS] * cumt_factor * q_factor;
+        R lo = S[US_LAMO], ll = S[US_LAML], ef = S[US_EFF];
+        if (r_abs(aecs - P[U_ECS]) > R(1e-10)) {
+            R lo2, ll2, ef2;
+            if (udeb_lamcalc(P, aecs, lo2, ll2, ef2)) { lo = lo2; ll = ll2; ef = ef2; }
+        }
+        X[UX_LAM * 32] = static_cast<double>(lo);
+        X[(UX_LAM + 1) * 32] = static_cast<double>(ll);
+        X[(UX_LAM + 2) * 32] = static_cast<double>(ef);
     }
+    __syncthreads();
+    const R lam_o = R(X[UX_LAM * 32]), lam_l = R(X[(UX_LAM + 1) * 32]), co2_eff = R(X[(UX_LAM + 2) * 32]);
+    if (R(X[UX_T0 * 32]) == R(0) && in[2] != R(0)) { // warm start from non-zero initial surface temperatures (mod.rs:439-448)
+        if (!bottom) T[0] = h ? in[4] : in[2];
+        S[US_LAND0] = in[3]; S[US_LAND1] = in[5];
+        S[US_GR0] = S[US_LAND0]; S[US_GR1] = S[US_LAND1];
+    }
+    X[(UX_EDGE + q) * 32] = static_cast<double>(T[0]); // edge temperatures for the first sub-step
+    __syncthreads();
     R area[4];
     udeb_fractions(P, area);
     const R fgno = area[0], fgnl = area[1], fgso = area[2], fgsl = area[3];
@@ -502,9 +522,13 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
             if (!(fgnl < R(1e-15))) S[US_GR0] += gr_c0 * (S[US_LAND0] - S[US_GR0]);
             if (!(fgsl < R(1e-15))) S[US_GR1] += gr_c1 * (S[US_LAND1] - S[US_GR1]);
         }
-        udeb_substep<R, N>(y, P, S, tab, bottom, h, mask, T, F, e * (h ? S[US_QF2] : S[US_QF0]));
-        sst_nh = __shfl_sync(mask, T[0], quad);
-        sst_sh = __shfl_sync(mask, T[0], quad + 1);
+        udeb_substep<R, N>(y, P, S, tab, q, X, T, F, e * (h ? S[US_QF2] : S[US_QF0]));
+        // one rendezvous serves two purposes: the new sea-surface temperatures for the land / upwelling updates below,
+        // and the edge temperatures (mixed layer, bottom layer) the next sub-step's sweeps start from
+        X[(UX_EDGE + q) * 32] = static_cast<double>(T[0]);
+        __syncthreads();
+        sst_nh = R(X[UX_EDGE * 32]);
+        sst_sh = R(X[(UX_EDGE + 1) * 32]);
         const R air_nho = udeb_sst_to_air(air, sst_nh), air_sho = udeb_sst_to_air(air, sst_sh);
         // calculate_land_temperature (mod.rs:352-375) with the year's reciprocal denominators
         S[US_LAND0] = udeb_cap((e * S[US_QF1] * fgnl + kla * air_nho) * inv_den_n, y.tmax);
@@ -515,16 +539,12 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         S[US_W0] = udeb_floor(w0 * (R(1) - fv * udeb_cap(gt * inv_wt_nh, R(1))), wmin_b);
         S[US_W1] = udeb_floor(w0 * (R(1) - fv * udeb_cap(gt * inv_wt_sh, R(1))), wmin_b);
     }
-    if (steps_n < 1) { // (rejected by the host; keeps sst defined)
-        sst_nh = __shfl_sync(mask, T[0], quad);
-        sst_sh = __shfl_sync(mask, T[0], quad + 1);
-    }
     S[US_AE0] = (r_abs(sst_nh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(air, sst_nh) / sst_nh;
     S[US_AE1] = (r_abs(sst_sh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(air, sst_sh) / sst_sh;
     const R st[4] = {udeb_sst_to_air(air, sst_nh), S[US_LAND0], udeb_sst_to_air(air, sst_sh), S[US_LAND1]};
     const R gt = st[0] * fgno + st[1] * fgnl + st[2] * fgso + st[3] * fgsl;
-    if (q == 0) cx.scratch[static_cast<long long>(nr.scr + nhist) * cx.runs] = static_cast<double>(gt * dt_year);
-    __syncwarp(mask); // next year the other lanes of the quad read this entry
+    // (the other roles read this entry next year, after the barriers of the node's entry)
+    if (q == 0 && cx.live) cx.scratch[static_cast<long long>(nr.scr + nhist) * cx.runs] = static_cast<double>(gt * dt_year);
     S[US_NHIST] = R(nhist + 1);
     R f_end[4];
     udeb_apply_efficacy(P, S, erf_end, co2_eff, f_end);
@@ -535,7 +555,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         out[0] = qq - fb;
     }
     {
-        // ocean heat content: every lane weighs its rows (the mixed layer is the top lanes' row 0), the quad adds up
+        // ocean heat content: every role weighs its rows (the mixed layer is the top roles' row 0), summed through the exchange
         const R rho_c = R(1026.0) * R(3985.0);
         R part = R(0);
         if (NB > NT) {
@@ -544,9 +564,9 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
 #pragma unroll
         for (int j = NT - 1; j >= 1; --j) part += T[j];
         part = rho_c * P[U_DZ] * part + rho_c * (bottom ? P[U_DZ] : P[U_MLD]) * T[0];
-        part += udeb_shx(mask, part, 1);
-        part += udeb_shx(mask, part, 2);
-        out[1] = part / R(2);
+        X[(UX_OHC + q) * 32] = static_cast<double>(part);
+        __syncthreads();
+        out[1] = ((R(X[UX_OHC * 32]) + R(X[(UX_OHC + 1) * 32])) + (R(X[(UX_OHC + 2) * 32]) + R(X[(UX_OHC + 3) * 32]))) / R(2);
     }
     out[2] = (sst_nh + sst_sh) / R(2);
     for (int i = 0; i < 4; ++i) out[3 + i] = st[i];

@@ -33,15 +33,23 @@ template <class R> struct StepCtx {
     long long runs, run;
     int Tpad;
     int N;                // current time index
-    int role;             // lane of this thread within its member's lane group (0 when Prog::LANES == 1)
+    // Lane groups (Prog::LANES == 4: programs with ClimateUDEB).  Each warp of the CTA is one ROLE of the CTA's 32
+    // members: lane l of every warp belongs to member l.  Role 0 runs the component graph thread-per-member; the kinds
+    // that spread a member over four threads (ClimateUDEB's half-sweeps, OceanCarbon's history sums) are entered by all
+    // four warps, which exchange through `xch` (shared memory) and __syncthreads().
+    int role;             // this thread's role = (warp + rot) & 3 (0 when Prog::LANES == 1)
+    int rot;              // role rotation of this CTA; role r of a member is thread ((r - rot) & 3) * 32 + lane
     int lanes;            // Prog::LANES
-    unsigned mask;        // the warp's lanes that step (shuffle mask for lane groups)
+    bool live;            // false for the padding members of the last CTA: they compute (barriers need every warp) but
+                          // must not write global scratch
+    double *xch;          // this member's exchange column: slot j at xch[j * 32]
 };
 
-// Per-node literals the emitter passes: RK4 table row, offsets into ctab / sm / scratch / gtab, and one
-// kind-specific integer (e.g. OceanCarbon's steps_per_year) that must be a compile-time constant.
+// Per-node literals the emitter passes: RK4 table row, offsets into ctab / sm / scratch / gtab, one kind-specific
+// integer (e.g. OceanCarbon's steps_per_year) that must be a compile-time constant, and the first exchange slot the
+// kind may use (lane groups; the slots before it carry the node's broadcast inputs).
 struct NodeRef {
-    int rk, ctab, sm, scr, gt, aux;
+    int rk, ctab, sm, scr, gt, aux, xch;
 };
 
 // ---------------------------------------------------------------------------

@@ -210,6 +210,7 @@ size_t smem_bytes(const rscm_b200_ensemble *h, bool logp)
     b += h->g.ctab.size() * 8;
     b += static_cast<size_t>(h->g.n_rk) * h->Tpad * 4;
     b += static_cast<size_t>(h->g.n_smem) * rscm_dev::BLOCK * 8; // n_smem counts 8-byte words per thread in both dtypes
+    b += static_cast<size_t>(h->g.n_xch) * 32 * 8;                // exchange area of lane-group programs
     return b;
 }
 
@@ -343,7 +344,7 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
         a.init_def[c] = var.has_initial ? var.initial : std::numeric_limits<double>::quiet_NaN();
         a.out_off[c] = (write && h->out_base[c] >= 0) ? static_cast<long long>(h->out_base[c]) * a.runs * 8 : -1;
     }
-    const int64_t members_per_cta = rscm_dev::BLOCK / g.lanes; // Prog::LANES threads work on one member
+    const int64_t members_per_cta = rscm_dev::BLOCK / g.lanes; // Prog::LANES threads (one per warp of the CTA) work on one member
     const dim3 grid(static_cast<unsigned>((M + members_per_cta - 1) / members_per_cta), static_cast<unsigned>(S));
     if (logp && d_summary) {
         const int64_t nb = static_cast<int64_t>(grid.x) * grid.y;

@@ -327,7 +327,7 @@ static const std::vector<KindInfo> &kinds()
          96, /*n_state: 19 scalars + this lane's 25 rows of the ocean column*/ 44, /*n_smem: eliminated off-diagonal of those rows*/ 25, /*scratch_per_T*/ 1, /*needs_time*/ true,
          /*in_access: erf at_start, erf at_end, surface temperature at_start*/ {{0, 1}, {0, 2}, {1, 1}}, &udeb_const_table, &udeb_window_table,
          /*aux_param: n_layers sizes the register rows*/ 0, /*scratch_fixed*/ 0, /*no_slots*/ false, /*lanes: 2 hemispheres x 2 sweep ends*/ 4,
-         /*aux_template*/ true},
+         /*aux_template*/ true, /*n_smem_lanes*/ 0, /*lane_aware*/ true, /*n_xch*/ 28},
         {RSCM_B200_FOUR_BOX_OHU, "FourBoxOceanHeatUptake", "four_box_ohu",
          // crates/rscm-components/src/components/four_box_ocean_heat_uptake.rs
          {{"Effective Radiative Forcing|Aggregated", REQ_INPUT, RSCM_B200_SCALAR}, {"Heat Uptake|Ocean", REQ_OUTPUT, RSCM_B200_FOUR_BOX}},
@@ -413,7 +413,7 @@ static const std::vector<KindInfo> &kinds()
           1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0},
          48, /*n_state*/ 1, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10,
          /*scratch_fixed*/ 0, /*no_slots*/ false, /*lanes*/ 1, /*aux_template*/ false,
-         /*n_smem_lanes: block-prefix sums of the convolution, one year per lane of a quad*/ 16},
+         /*n_smem_lanes: block-prefix sums of the convolution, one year of the block per role*/ 16, /*lane_aware*/ true, /*n_xch*/ 0},
     };
     static const bool extended = (k.push_back(halocarbon_kind()), true);
     (void)extended;
@@ -536,6 +536,7 @@ static void emit_program(Graph &g)
     o << "    static constexpr int NS = " << g.n_state << ";\n";
     o << "    static constexpr int NSM = " << g.n_smem << ";\n";
     o << "    static constexpr int LANES = " << g.lanes << ";\n";
+    o << "    static constexpr int NXCH = " << g.n_xch << ";\n";
     o << "    static constexpr bool SYNC_STEPS = " << (g.n_cells > 64 ? "true" : "false") << ";\n";
     o << "    static constexpr bool NEEDS_TIME = " << (g.needs_time ? "true" : "false") << ";\n";
     // exogenous rows are staged into shared memory unless per-thread scratch or a long row list needs the space
@@ -585,7 +586,7 @@ static void emit_program(Graph &g)
     auto node_ref = [](const Node &n) {
         std::ostringstream s;
         s << "rscm_dev::NodeRef{" << (n.rk_table >= 0 ? n.rk_table : 0) << ", " << n.ctab_base << ", " << n.smem_base << ", "
-          << n.scratch_base << ", " << n.gtab_base << ", " << n.aux << "}";
+          << n.scratch_base << ", " << n.gtab_base << ", " << n.aux << ", " << n.xch_user << "}";
         return s.str();
     };
     o << "    template <class R> __device__ __forceinline__ static void init_state(const R *P, const R *D, R *S,\n"
@@ -603,9 +604,12 @@ static void emit_program(Graph &g)
          "                                                                  const rscm_dev::StepCtx<R> &cx, unsigned &fail) {\n";
     o << "        (void)P; (void)D; (void)cur; (void)S; (void)cx; (void)fail;\n";
     int tmp_id = 0;
+    // lane-group programs: role 0 (warp 0) runs the graph; lane nodes are entered by every role
+    const bool lanes = g.lanes > 1;
     for (int ni : g.order) {
         const Node &n = g.nodes[ni];
-        o << "      { // node " << ni << "\n";
+        const bool lane_node = lanes && n.kind != KIND_AGGREGATOR && n.lane_node;
+        o << "      " << (lanes && !lane_node ? "if (cx.role == 0) " : "") << "{ // node " << ni << "\n";
         std::ostringstream pre;
         if (n.kind == KIND_AGGREGATOR) {
             // AggregatorComponent::solve — schema.rs:874-951: contributors read at_end
@@ -656,14 +660,38 @@ static void emit_program(Graph &g)
             }
             int n_out_vals = 0;
             for (size_t i = 0; i < n.out_var.size(); ++i) n_out_vals += grid_regions(n.out_grid[i]);
+            const std::string solve_call = std::string("rscm_dev::") + k->dev_name + "_solve<R" + (k->aux_template ? ", " + std::to_string(n.aux) : std::string()) +
+                                           ">(P + " + std::to_string(n.param_base) + ", D + " + std::to_string(n.derived_base) + ", in, out, cx, S + " +
+                                           std::to_string(n.state_base) + ", " + node_ref(n) + ")";
+            if (lane_node) {
+                // role 0 evaluates the inputs from its cells and publishes them; the other roles pick them up
+                const size_t nin = in_exprs.empty() ? 1 : in_exprs.size();
+                o << "        R in[" << nin << "];\n";
+                o << "        if (cx.role == 0) {\n" << pre.str();
+                for (size_t i = 0; i < in_exprs.size(); ++i) {
+                    o << "          in[" << i << "] = " << in_exprs[i] << ";\n";
+                    o << "          cx.xch[" << (n.xch_base + static_cast<int>(i)) * 32 << "] = static_cast<double>(in[" << i << "]);\n";
+                }
+                if (in_exprs.empty()) o << "          in[0] = R(0);\n";
+                o << "        }\n        __syncthreads();\n";
+                o << "        if (cx.role != 0) {\n";
+                for (size_t i = 0; i < in_exprs.size(); ++i)
+                    o << "          in[" << i << "] = R(cx.xch[" << (n.xch_base + static_cast<int>(i)) * 32 << "]);\n";
+                if (in_exprs.empty()) o << "          in[0] = R(0);\n";
+                o << "        }\n";
+                o << "        R out[" << n_out_vals << "];\n";
+                o << "        const bool ok = " << solve_call << ";\n";
+                o << "        __syncthreads(); // every role has left the node before role 0 reuses the exchange slots\n";
+                o << "        if (cx.role == 0) {\n        if (ok) {\n";
+            } else {
             o << pre.str();
             o << "        const R in[" << (in_exprs.empty() ? 1 : in_exprs.size()) << "] = {";
             for (size_t i = 0; i < in_exprs.size(); ++i) o << (i ? ", " : "") << in_exprs[i];
             if (in_exprs.empty()) o << "R(0)";
             o << "};\n";
             o << "        R out[" << n_out_vals << "];\n";
-            o << "        if (rscm_dev::" << k->dev_name << "_solve<R" << (k->aux_template ? ", " + std::to_string(n.aux) : std::string()) << ">(P + " << n.param_base << ", D + " << n.derived_base
-              << ", in, out, cx, S + " << n.state_base << ", " << node_ref(n) << ")) {\n";
+            o << "        if (" << solve_call << ") {\n";
+            }
             int pos = 0;
             for (size_t i = 0; i < n.out_var.size(); ++i) {
                 const Variable &var = g.vars[n.out_var[i]];
@@ -693,6 +721,7 @@ static void emit_program(Graph &g)
                 for (int r = 0; r < var.n_regions; ++r) o << "            nxt[" << (var.cell0 + r) << "] = rscm_dev::r_nan<R>();\n";
             }
             o << "        }\n";
+            if (lane_node) o << "        }\n";
         }
         o << "      }\n";
     }
@@ -965,6 +994,18 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         n.ctab_base = static_cast<int>(g.ctab.size());
         g.n_state += k->n_state;
         g.n_smem += k->n_smem + (g.lanes > 1 ? k->n_smem_lanes : 0);
+        if (g.lanes > 1 && (k->lanes > 1 || k->lane_aware)) {
+            // a lane node: its input values travel from role 0 to the other roles through the first exchange slots
+            n.lane_node = true;
+            int n_in_vals = 0;
+            std::vector<std::pair<int, int>> access = k->in_access;
+            if (access.empty())
+                for (size_t i = 0; i < n.in_var.size(); ++i) access.push_back({static_cast<int>(i), 0});
+            for (const auto &ac : access) n_in_vals += grid_regions(n.in_grid[ac.first]);
+            n.xch_base = g.n_xch;
+            n.xch_user = g.n_xch + n_in_vals;
+            g.n_xch += n_in_vals + k->n_xch;
+        }
         g.n_scratch_rows += k->scratch_fixed + k->scratch_per_T * g.T;
         g.needs_time = g.needs_time || k->needs_time;
         if (k->const_table) {

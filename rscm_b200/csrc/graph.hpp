@@ -54,6 +54,11 @@ struct KindInfo {
     int lanes = 1; // lanes of a warp that work on one member (ClimateUDEB: 4); the program takes the largest of its kinds
     bool aux_template = false; // the aux literal is also a template argument of <dev_name>_solve / _init_state
     int n_smem_lanes = 0; // extra per-thread shared-memory words when the PROGRAM runs lane groups (Prog::LANES > 1)
+    // In a lane-group program only role 0 (warp 0 of the CTA) runs the component graph; a kind with lanes > 1 or
+    // lane_aware is entered by all four warps: the emitter broadcasts its inputs through the exchange area, the kind
+    // may use n_xch further exchange slots (doubles per member) of its own.
+    bool lane_aware = false;
+    int n_xch = 0;
 };
 
 const KindInfo *kind_info(int kind);
@@ -79,6 +84,8 @@ struct Node {
     int derived_base = 0; // first derived-constant slot
     int rk_table = -1;    // row of the sub-step table
     int state_base = 0, smem_base = 0, scratch_base = 0, ctab_base = 0; // offsets of this node's stateful storage
+    int xch_base = 0, xch_user = 0; // exchange slots of a lane node: broadcast inputs from xch_base, the kind's own from xch_user
+    bool lane_node = false; // entered by all roles of a lane-group program
     int gtab_base = 0, aux = 0;
     std::vector<int> in_var, in_src, in_grid;
     std::vector<double> in_factor;
@@ -98,6 +105,7 @@ struct Graph {
     std::vector<int> exo_vars;  // variable ids, scenario order
     int n_cells = 0, n_slots = 0, n_derived = 0, n_exo_rows = 0, n_rk = 0;
     int lanes = 1;         // Prog::LANES: threads per member
+    int n_xch = 0;         // Prog::NXCH: exchange slots (doubles per member) of a lane-group program
     bool stage_exo = true; // Prog::STAGE_EXO: exogenous rows staged in shared memory (else read from global)
     int n_state = 0, n_smem = 0, n_scratch_rows = 0; // stateful components: totals (scratch rows already x T)
     bool needs_time = false;

@@ -228,7 +228,10 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     double *s_bounds = s_obs + static_cast<unsigned long long>(LOGP ? 2 * a.n_obs_rows : 0) * a.Tpad;
     double *s_ctab = s_bounds + (Prog::NEEDS_TIME ? a.Tpad + 4 : 0);
     int *s_nsub = reinterpret_cast<int *>(s_ctab + a.n_ctab);
-    R *s_thread = reinterpret_cast<R *>(s_nsub + static_cast<unsigned long long>(a.n_rk) * a.Tpad) + threadIdx.x;
+    R *s_thread0 = reinterpret_cast<R *>(s_nsub + static_cast<unsigned long long>(a.n_rk) * a.Tpad);
+    R *s_thread = s_thread0 + threadIdx.x;
+    // exchange area of lane-group programs: [Prog::NXCH][32] doubles after the per-thread scratch ([NSM][BLOCK] 8-byte words)
+    double *s_xch = reinterpret_cast<double *>(s_thread0) + static_cast<unsigned long long>(Prog::NSM) * BLOCK;
 
     const unsigned exo_bytes = STAGE_EXO ? static_cast<unsigned>(a.n_exo_rows) * a.Tpad * 8u : 0u;
     const double *x_exo = STAGE_EXO ? s_exo : a.exo + static_cast<unsigned long long>(blockIdx.y) * a.n_exo_rows * a.Tpad;
@@ -251,13 +254,18 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     }
 
     // ---- per-member parameters (coalesced SoA loads overlap the bulk copies) ----
-    // Prog::LANES lanes work on one member (ClimateUDEB: 4, see climate_udeb.cuh); a CTA then holds BLOCK / LANES members
+    // Prog::LANES threads work on one member (programs with ClimateUDEB: 4, see StepCtx in components.cuh): warp w of the
+    // CTA is role w of the CTA's 32 members, warp 0 also runs the rest of the component graph thread-per-member
     constexpr int LANES = Prog::LANES;
-    const int role = LANES == 1 ? 0 : static_cast<int>(threadIdx.x) % LANES;
-    const long long m_raw = static_cast<long long>(blockIdx.x) * (BLOCK / LANES) + threadIdx.x / LANES;
+    static_assert(LANES == 1 || BLOCK / LANES == 32, "a lane group is one lane of each warp of the CTA");
+    // Warp w goes to scheduler w % 4 of its SM: were role 0 always warp 0, one scheduler would carry the graph work of
+    // every resident CTA.  The roles are rotated by CTA (148 SMs: the CTAs that share an SM differ by multiples of 148).
+    const int rot = LANES == 1 ? 0 : static_cast<int>((blockIdx.x + blockIdx.x / 148u) & 3u);
+    const int role = LANES == 1 ? 0 : ((static_cast<int>(threadIdx.x) >> 5) + rot) & 3;
+    const long long m_raw = LANES == 1 ? static_cast<long long>(blockIdx.x) * BLOCK + threadIdx.x
+                                       : static_cast<long long>(blockIdx.x) * 32 + (threadIdx.x & 31);
     const bool active = m_raw < a.M;
-    const bool writer = active && role == 0; // the lane that stores the member's outputs
-    const unsigned step_mask = __ballot_sync(0xffffffffu, active);
+    const bool writer = active && role == 0; // the thread that stores the member's outputs
     const long long m = active ? m_raw : a.M - 1;
     const long long run = static_cast<long long>(blockIdx.y) * a.M + m;
     const double *pm = a.params + m * a.ld_mem;
@@ -288,7 +296,8 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     if (total_bytes) mbar_wait(bar, 0);
     // Padding threads of the last CTA (clamped to run M-1) are only needed for the block-wide reductions of the
     // log-posterior variants; they must not step (they would race with the real run on its global scratch rows).
-    if (!LOGP && !active) return;
+    // (lane-group programs synchronise their warps inside the step: their padding members step too, without side effects)
+    if (LANES == 1 && !LOGP && !active) return;
 
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -310,9 +319,11 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     cx.N = 0;
     cx.role = role;
     cx.lanes = LANES;
-    cx.mask = step_mask;
+    cx.live = active;
+    cx.rot = rot;
+    cx.xch = s_xch + (threadIdx.x & 31);
     R S[Prog::NS > 0 ? Prog::NS : 1];
-    if (!LOGP || active) Prog::template init_state<R>(P, D, S, cx);
+    if (LANES > 1 || !LOGP || active) Prog::template init_state<R>(P, D, S, cx);
 
     double ll[MAX_OBS_ROWS] = {0.0, 0.0, 0.0, 0.0};
     bool bad = false;
@@ -345,14 +356,14 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
         // Programs whose step is far larger than the instruction cache (the 124-variable MAGICC chain: 128 KB of SASS per
         // model year) keep the warps of a CTA in step, so that they fetch the same instructions together instead of
         // streaming four copies.  (Padding threads have exited or skip the step; a barrier counts non-exited threads.)
-        if (Prog::SYNC_STEPS) __syncthreads();
+        if (Prog::SYNC_STEPS && LANES == 1) __syncthreads();
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(x_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
             else if (Prog::nan_init(c)) nxt[c] = r_nan<R>(); // other cells are overwritten on every path of the step
         }
         cx.N = N;
-        if (!LOGP || active) Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
+        if (LANES > 1 || !LOGP || active) Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
 
         if (WRITE) {
             if (N + 1 == tnext && tnext < a.t_stop) { // block-uniform

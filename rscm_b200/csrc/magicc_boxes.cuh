@@ -186,12 +186,13 @@ __device__ __forceinline__ bool n2o_chemistry_solve(const R *P, const R *, const
 // in the member-interleaved global scratch, and the partial sums of all `steps` months of a year are advanced together
 // (steps FMAs per load) in the reference's oldest-to-newest order, so the sums are the same up to FMA contraction.
 //   * one thread per member (Prog::LANES == 1): the history that predates the current year is read once per year;
-//   * lane quads (a program with ClimateUDEB): years are taken in blocks of four.  At the first year of a block lane q
-//     sums the whole history that predates the block against the lags of the block's year q (12 prefix sums, kept in
-//     this lane's shared-memory column); every year then starts from the prefix sums of its lane and adds the block's
-//     own months.  The long history is read once per FOUR years and by four lanes at once (it is the HBM traffic
-//     that bounds the emissions-driven chain: 4200 months x 8 B per member at the end of a 350-year run), the
-//     accumulation order per month is unchanged (history before the block, then the block, oldest first).
+//   * lane groups (a program with ClimateUDEB: four warps = four roles per member, StepCtx): years are taken in
+//     blocks of four.  At the first year of a block role q sums the whole history that predates the block against the
+//     lags of the block's year q (12 prefix sums, kept in this thread's shared-memory column); role 0 then steps every
+//     year from the prefix sums of that year's role and adds the block's own months.  The long history is read once per
+//     FOUR years and by four warps at once (it is the HBM traffic that bounds the emissions-driven chain: 4200 months
+//     x 8 B per member at the end of a 350-year run); the accumulation order per month is unchanged (history before
+//     the block, then the block, oldest first).
 // P: see include/rscm_b200.h (60 values); S[0] = months of history so far.
 template <class R> __device__ __forceinline__ void ocean_carbon_prepare(const R *P, R *D)
 {
@@ -246,10 +247,10 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     // a flux older than max_history_months has left the reference's deque: no need to load it (its weights are zero)
     const int max_hist = static_cast<int>(P[11]);
     if (cx.lanes == 4) {
-        R *A = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R))); // this lane's prefix sums, month m at A[m * BLOCK]
-        const int yb = (n_old / steps) & 3;                               // year within the block of four
+        R *A = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R))); // this thread's prefix sums, month m at A[m * BLOCK]
+        const int yb = (n_old / steps) & 3;                               // year within the block of four (CTA-uniform)
         if (yb == 0) {
-            const int first_month = n_old + steps * cx.role;              // lane q prepares year q of the block
+            const int first_month = n_old + steps * cx.role;              // role q prepares year q of the block
 #pragma unroll
             for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
             const int lo = first_month + 1 - max_hist;
@@ -257,9 +258,14 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
 #pragma unroll
             for (int m = 0; m < MAXS; ++m)
                 if (m < steps) A[m * BLOCK] = acc[m];
-            __syncwarp(cx.mask);
         }
-        const R *Ay = A + (yb - cx.role); // the column of the lane that prepared this year (same quad, same warp)
+        __syncthreads();
+        if (cx.role != 0) { // the other roles only help with the long history; role 0 steps the months
+            S[0] = R(n_old + steps);
+            return true;
+        }
+        // the column of the role that prepared this year: thread ((yb - rot) & 3) * 32 + lane, this one (role 0) is ((-rot) & 3) * 32 + lane
+        const R *Ay = A + ((((yb - cx.rot) & 3) - ((-cx.rot) & 3)) * 32);
 #pragma unroll
         for (int m = 0; m < MAXS; ++m) acc[m] = (m < steps) ? Ay[m * BLOCK] : R(0);
         convolve(n_old - yb * steps, n_old, n_old); // the block's own months so far (just written: L1 / L2 resident)
@@ -276,7 +282,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     for (int m = 0; m < MAXS; ++m) {
         if (m < steps) {
             const R flux_ppm = k_gas * (co2 - pco2);
-            if (cx.role == 0) hist[static_cast<long long>(n_old + m) * cx.runs] = static_cast<double>(flux_ppm);
+            if (cx.live) hist[static_cast<long long>(n_old + m) * cx.runs] = static_cast<double>(flux_ppm);
             fy[m] = flux_ppm;
             const R flux_gtc_yr = flux_ppm * R(12) * R(2.124);
             total_flux += flux_gtc_yr / R(steps);
@@ -294,7 +300,6 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
             pco2 = (P[2] + dp) * tfac;
         }
     }
-    if (cx.lanes > 1) __syncwarp(cx.mask); // the other lanes of the quad read these months next year
     S[0] = R(n_old + steps);
     out[0] = total_flux;
     out[1] = pco2;
