@@ -117,6 +117,18 @@ __device__ __forceinline__ double rscm_log(double y)
     return fma(ed, RSCM_LOG_C[0], t23.x + (r + fma(ed, RSCM_LOG_C[1], t23.y)));
 }
 
+// Out-of-line copies for the components of large programs (the MAGICC boxes): a call is a handful of instructions where
+// the inlined function is forty, and those programs are bound by instruction fetch.  The two-component
+// programs of the headline path keep the inlined versions.
+__device__ __noinline__ double rscm_exp_call(double x) { return rscm_exp(x); }
+__device__ __noinline__ double rscm_log_call(double y) { return rscm_log(y); }
+template <class R> __device__ __forceinline__ R r_exp_call(R x);
+template <> __device__ __forceinline__ double r_exp_call<double>(double x) { return rscm_exp_call(x); }
+template <> __device__ __forceinline__ float r_exp_call<float>(float x) { return expf(x); }
+template <class R> __device__ __forceinline__ R r_log_call(R x);
+template <> __device__ __forceinline__ double r_log_call<double>(double x) { return rscm_log_call(x); }
+template <> __device__ __forceinline__ float r_log_call<float>(float x) { return logf(x); }
+
 template <class R> __device__ __forceinline__ R r_exp(R x);
 template <> __device__ __forceinline__ double r_exp<double>(double x) { return rscm_exp(x); }
 template <> __device__ __forceinline__ float r_exp<float>(float x) { return expf(x); }
@@ -127,7 +139,10 @@ template <class R> __device__ __forceinline__ R r_sqrt(R x);
 template <> __device__ __forceinline__ double r_sqrt<double>(double x) { return sqrt(x); }
 template <> __device__ __forceinline__ float r_sqrt<float>(float x) { return sqrtf(x); }
 template <class R> __device__ __forceinline__ R r_pow(R x, R y);
-template <> __device__ __forceinline__ double r_pow<double>(double x, double y) { return pow(x, y); }
+// pow() inlines to a few hundred instructions per call site; the MAGICC chain has fourteen of them per model year, half of
+// its per-year code, which is already far larger than the instruction cache: one out-of-line copy instead
+__device__ __noinline__ double rscm_pow(double x, double y) { return pow(x, y); }
+template <> __device__ __forceinline__ double r_pow<double>(double x, double y) { return rscm_pow(x, y); }
 template <> __device__ __forceinline__ float r_pow<float>(float x, float y) { return powf(x, y); }
 template <class R> __device__ __forceinline__ R r_nan();
 template <> __device__ __forceinline__ double r_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -313,7 +328,7 @@ template <class R> __device__ __forceinline__ void ghg_forcing_prepare(const R *
 template <class R> __device__ __forceinline__ R ghg_overlap_f(R ch4, R n2o)
 {
     const R mn = ch4 * n2o;
-    return R(0.47) * r_log<R>(R(1) + R(2.01e-5) * r_pow<R>(mn, R(0.75)) +
+    return R(0.47) * r_log_call<R>(R(1) + R(2.01e-5) * r_pow<R>(mn, R(0.75)) +
                               R(5.31e-15) * ch4 * r_pow<R>(mn, R(1.52)));
 }
 
@@ -323,7 +338,7 @@ __device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *, const R
     const R co2 = in[0], ch4 = in[1], n2o = in[2];
     R co2_raw, ch4_raw, n2o_raw;
     if (P[0] == R(0)) { // Ipcctar, ghg.rs:164-200
-        co2_raw = (P[4] / R(0.6931471805599453094172321)) * r_log<R>(co2 / P[1]);
+        co2_raw = (P[4] / R(0.6931471805599453094172321)) * r_log_call<R>(co2 / P[1]);
         ch4_raw = P[5] * (r_sqrt<R>(ch4) - r_sqrt<R>(P[2])) -
                   (ghg_overlap_f<R>(ch4, P[3]) - ghg_overlap_f<R>(P[2], P[3]));
         n2o_raw = P[6] * (r_sqrt<R>(n2o) - r_sqrt<R>(P[3])) -
@@ -337,7 +352,7 @@ __device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *, const R
         if (co2 >= c_max) alpha = -b1 * b1 / (R(4) * a1) + d1 + n2o_overlap;
         else if (co2 <= co2_pi) alpha = d1 + n2o_overlap;
         else alpha = a1 * delta * delta + b1 * delta + d1 + n2o_overlap;
-        co2_raw = alpha * r_log<R>(co2 / co2_pi);
+        co2_raw = alpha * r_log_call<R>(co2 / co2_pi);
         const R s_ch4 = r_sqrt<R>(ch4), s_n2o = r_sqrt<R>(n2o), s_co2 = r_sqrt<R>(co2);
         ch4_raw = (P[11] * s_ch4 + P[12] * s_n2o + P[13]) * (s_ch4 - r_sqrt<R>(P[2]));
         n2o_raw = (P[14] * s_co2 + P[15] * s_n2o + P[16] * s_ch4 + P[17]) * (s_n2o - r_sqrt<R>(P[3]));
@@ -361,7 +376,7 @@ __device__ __forceinline__ bool ozone_forcing_solve(const R *P, const R *, const
 {
     const R delta_eesc = in[0] - P[0];
     out[0] = (delta_eesc <= R(0)) ? R(0) : P[1] * r_pow<R>(delta_eesc / R(100), P[2]);
-    const R ch4_term = (in[1] > R(0) && P[8] > R(0)) ? P[4] * r_log<R>(in[1] / P[8]) : R(0);
+    const R ch4_term = (in[1] > R(0) && P[8] > R(0)) ? P[4] * r_log_call<R>(in[1] / P[8]) : R(0);
     const R precursor = P[5] * (in[2] - P[9]) + P[6] * (in[3] - P[10]) + P[7] * (in[4] - P[11]);
     out[1] = P[3] * (ch4_term + precursor);
     out[2] = P[12] * in[5];
@@ -408,7 +423,7 @@ __device__ __forceinline__ bool aerosol_indirect_solve(const R *P, const R *, co
     const R burden = P[2] * in[0] + P[3] * in[1];
     const R burden_pi = P[2] * P[4] + P[3] * P[5];
     const R delta = burden - burden_pi;
-    out[0] = (delta <= R(0)) ? R(0) : P[0] * r_log<R>(R(1) + delta / P[1]);
+    out[0] = (delta <= R(0)) ? R(0) : P[0] * r_log_call<R>(R(1) + delta / P[1]);
     return true;
 }
 

@@ -30,7 +30,7 @@ __device__ __forceinline__ bool ocean_surface_pp_solve(const R *P, const R *, co
     R dot = R(0);
 #pragma unroll
     for (int i = 0; i < 5; ++i) dot += (P[3 + i] + P[8 + i] * P[2]) * bits[i];
-    out[0] = (P[0] + dot) * r_exp<R>(P[1] * in[0]);
+    out[0] = (P[0] + dot) * r_exp_call<R>(P[1] * in[0]);
     return true;
 }
 
@@ -79,13 +79,13 @@ __device__ __forceinline__ bool terrestrial_carbon_solve(const R *P, const R *D,
     const R co2 = in[0], temperature = in[1], landuse = in[2];
     const R dt = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
     R fert = R(1);
-    if (P[18] != R(0) && !(co2 <= R(0))) fert = r_max(R(1) + P[2] * r_log<R>(co2 / P[1]), R(0.1));
+    if (P[18] != R(0) && !(co2 <= R(0))) fert = r_max(R(1) + P[2] * r_log_call<R>(co2 / P[1]), R(0.1));
     const bool tf = P[19] != R(0);
-    const R npp = P[0] * fert * (tf ? r_exp<R>(P[3] * temperature) : R(1));
-    const R respiration = P[12] * fert * (tf ? r_exp<R>(P[4] * temperature) : R(1));
-    const R tf_det = tf ? r_exp<R>(P[5] * temperature) : R(1);
-    const R tf_soil = tf ? r_exp<R>(P[6] * temperature) : R(1);
-    const R tf_hum = tf ? r_exp<R>(P[7] * temperature) : R(1);
+    const R npp = P[0] * fert * (tf ? r_exp_call<R>(P[3] * temperature) : R(1));
+    const R respiration = P[12] * fert * (tf ? r_exp_call<R>(P[4] * temperature) : R(1));
+    const R tf_det = tf ? r_exp_call<R>(P[5] * temperature) : R(1);
+    const R tf_soil = tf ? r_exp_call<R>(P[6] * temperature) : R(1);
+    const R tf_hum = tf ? r_exp_call<R>(P[7] * temperature) : R(1);
     R new_plant, to_plant, new_det, to_det, new_soil, to_soil, new_hum, to_hum;
     tc_pool_step<R>(in[3], D[0], npp * P[13] - respiration - landuse, R(1), dt, new_plant, to_plant);
     tc_pool_step<R>(in[4], D[1], npp * P[14] + P[15] * to_plant, tf_det, dt, new_det, to_det);
@@ -116,7 +116,7 @@ __device__ __forceinline__ bool ch4_chemistry_solve(const R *P, const R *D, cons
     const R tau_other = D[0];
     R base = P[2];
     if (P[13] != R(0))
-        base = P[2] * r_exp<R>(-P[7] * (P[8] * (in[2] - P[15]) + P[9] * (in[3] - P[16]) + P[10] * (in[4] - P[17])));
+        base = P[2] * r_exp_call<R>(-P[7] * (P[8] * (in[2] - P[15]) + P[9] * (in[3] - P[16]) + P[10] * (in[4] - P[17])));
     const R x = -P[7] * P[6];
     R burden = ch4_current * P[14], delta_burden = R(0), tau_oh = P[2];
 #pragma unroll
@@ -277,7 +277,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     }
     R fy[MAXS];
     R total_flux = R(0);
-    const R tfac = (P[59] != R(0)) ? r_exp<R>(P[5] * dsst) : R(1);
+    const R tfac = (P[59] != R(0)) ? r_exp_call<R>(P[5] * dsst) : R(1);
 #pragma unroll
     for (int m = 0; m < MAXS; ++m) {
         if (m < steps) {
@@ -336,14 +336,16 @@ __device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R 
     R total = R(0), fgas = R(0), montreal = R(0), eesc = R(0);
     // on a uniform time axis the decay factors are constants of the graph (host-computed, graph.cpp)
     const bool uniform_dt = static_cast<double>(dt) == tab[HALO_CT * HALO_NS];
-#pragma unroll
+    // One ROLLED loop over the 41 species: unrolled it is 3.5 k instructions of a program that is bound by instruction
+    // fetch.  The dynamic indices put in / out / S of this component into local memory (L1-resident: 4 doubles per species).
+#pragma unroll 1
     for (int s = 0; s < HALO_NS; ++s) {
         const double *t = tab + HALO_CT * s;
         const R lifetime = R(t[0]), conv = R(t[1]), rad_eff = R(t[2]), conc_pi = R(t[3]), loading = R(t[4]), release = R(t[5]);
         R conc = in[2 * s + 1];
         if (conc != conc) conc = S[s]; // latest_value: fall back to the last non-NaN value (NaN if there never was one)
         S[s] = conc;
-        const R decay = uniform_dt ? R(tab[HALO_CT * HALO_NS + 1 + s]) : r_exp<R>(-dt / lifetime); // block-uniform choice
+        const R decay = uniform_dt ? R(tab[HALO_CT * HALO_NS + 1 + s]) : r_exp_call<R>(-dt / lifetime); // block-uniform choice
         const R emissions_ppt = in[2 * s] * conv;
         const R new_conc = conc * decay + emissions_ppt * lifetime * (R(1) - decay);
         out[s] = new_conc;
