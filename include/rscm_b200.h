@@ -308,6 +308,9 @@ int64_t rscm_b200_launch_count(const rscm_b200_ensemble *h);
 /* average device time (ms, CUDA events on the launch stream) of the main fused
  * kernel over the launches since the last reset; 0 if none */
 double rscm_b200_kernel_ms(rscm_b200_ensemble *h, int reset);
+/* dynamic shared memory (bytes) one CTA of the fused kernel asks for (log_posterior != 0: the variant that also stages
+ * the observation tables): with the kernel's register count this fixes how many CTAs an SM holds */
+int64_t rscm_b200_shared_bytes(const rscm_b200_ensemble *h, int log_posterior);
 /* DFMA-saturating micro-benchmark: measured FP64 (or FP32 when dtype=1) FMA
  * throughput of `device` in TFLOP/s (2 flop per FMA) */
 int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops);

@@ -153,6 +153,7 @@ SYMBOLS = {
     "rscm_b200_logpost_device": (C.c_int, [_H, _PD, C.c_int64, C.c_int, _PD, C.c_int64, _PD, C.c_void_p, C.c_void_p]),
     "rscm_b200_logpost_host": (C.c_int, [_H, _PD, C.c_int64, C.c_int, _PD, C.c_int64, _PD, C.POINTER(LogpostSummary)]),
     "rscm_b200_launch_count": (C.c_int64, [_H]),
+    "rscm_b200_shared_bytes": (C.c_int64, [_H, C.c_int]),
     "rscm_b200_kernel_ms": (C.c_double, [_H, C.c_int]),
     "rscm_b200_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "rscm_b200_interpolate_device": (C.c_int, [_PD, C.c_int64, _PD, C.c_int64, C.c_int, _PD, C.c_int64, C.c_int, _PD, C.c_void_p]),

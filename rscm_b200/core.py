@@ -637,6 +637,10 @@ class Ensemble:
     def launch_count(self) -> int:
         return int(_ffi.lib.rscm_b200_launch_count(self._h))
 
+    def shared_bytes(self, log_posterior: bool = False) -> int:
+        """Dynamic shared memory per CTA of the fused kernel."""
+        return int(_ffi.lib.rscm_b200_shared_bytes(self._h, 1 if log_posterior else 0))
+
     def kernel_ms(self, reset: bool = False) -> float:
         return float(_ffi.lib.rscm_b200_kernel_ms(self._h, 1 if reset else 0))
 

@@ -430,11 +430,11 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
                 else { partial = rem / dt; rem = R(0); }
             }
         }
-        const double *hist = cx.scratch + static_cast<long long>(nr.scr) * cx.runs;
+        const double *hist = cx.scratch + static_cast<long long>(nr.scr) * SCR_LD;
         R sum = R(0);
 #pragma unroll 4
-        for (int i = nhist - 1 - q; i >= first; i -= UDEB_LANES) sum += R(hist[static_cast<long long>(i) * cx.runs]);
-        if (q == 0 && partial > R(0) && first > 0) sum += R(hist[static_cast<long long>(first - 1) * cx.runs]) * partial;
+        for (int i = nhist - 1 - q; i >= first; i -= UDEB_LANES) sum += R(hist[i * SCR_LD]);
+        if (q == 0 && partial > R(0) && first > 0) sum += R(hist[(first - 1) * SCR_LD]) * partial;
         X[(UX_HIST + q) * 32] = static_cast<double>(sum);
         if (q == 0) X[UX_T0 * 32] = static_cast<double>(T[0]); // the NH mixed-layer temperature (warm-start test below)
     }
@@ -544,7 +544,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     const R st[4] = {udeb_sst_to_air(air, sst_nh), S[US_LAND0], udeb_sst_to_air(air, sst_sh), S[US_LAND1]};
     const R gt = st[0] * fgno + st[1] * fgnl + st[2] * fgso + st[3] * fgsl;
     // (the other roles read this entry next year, after the barriers of the node's entry)
-    if (q == 0 && cx.live) cx.scratch[static_cast<long long>(nr.scr + nhist) * cx.runs] = static_cast<double>(gt * dt_year);
+    if (q == 0 && cx.live) cx.scratch[static_cast<long long>(nr.scr + nhist) * SCR_LD] = static_cast<double>(gt * dt_year);
     S[US_NHIST] = R(nhist + 1);
     R f_end[4];
     udeb_apply_efficacy(P, S, erf_end, co2_eff, f_end);

@@ -20,6 +20,49 @@
 namespace rscm_dev {
 
 constexpr int BLOCK = 128; // threads per CTA = stride of the per-thread shared-memory scratch
+constexpr int SCR_LD = 32;  // global scratch: runs are blocked by 32, row j of a block at j * SCR_LD (KArgs::scratch)
+
+// ---- mbarrier / TMA bulk-copy primitives (PTX) -----------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// Global memory written with ordinary stores and later read by a bulk copy (the async proxy): the writer fences, then
+// synchronises with the thread that issues the copy.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // What a component's solve sees beyond its own operands.
 template <class R> struct StepCtx {
@@ -28,9 +71,8 @@ template <class R> struct StepCtx {
     const double *ctab;   // per-graph constant tables (shared memory)
     const double *gtab;   // large per-graph constant tables (global memory, read through the read-only path)
     R *sm;                // this thread's shared-memory scratch: element j at sm[j * BLOCK]
-    double *scratch;      // this run's global scratch: element j at scratch[j * runs]
-    double *scratch0;     // the launch's global scratch (row j of all runs at scratch0 + j * runs)
-    long long runs, run;
+    double *scratch;      // this run's global scratch: element j at scratch[j * SCR_LD] (blocks of 32 runs, see KArgs::scratch)
+    int col;              // this run's column in its block of the global scratch (= member & 31)
     int Tpad;
     int N;                // current time index
     // Lane groups (Prog::LANES == 4: programs with ClimateUDEB).  Each warp of the CTA is one ROLE of the CTA's 32

@@ -311,7 +311,8 @@ int enqueue(rscm_b200_ensemble *h, const double *d_params, int64_t M, int layout
     a.n_ctab = static_cast<int>(g.ctab.size());
     if (g.n_scratch_rows > 0) {
         // global scratch of stateful components, one buffer per launch stream slot
-        const int64_t need = static_cast<int64_t>(g.n_scratch_rows) * S * M;
+        const int64_t need = static_cast<int64_t>(g.n_scratch_rows) * S * ((M + 31) / 32) * 32; // blocks of 32 members (KArgs::scratch)
+        a.scratch_rows = g.n_scratch_rows;
         const int slot = (st == h->streams[1] && st) ? 1 : 0;
         if (need > h->cap_scratch[slot]) {
             if (capturing) return fail(h, RSCM_B200_EINVAL, "scratch would have to grow inside a stream capture");
@@ -921,6 +922,8 @@ int rscm_b200_logpost_host(rscm_b200_ensemble *h, const double *params, int64_t 
 }
 
 int64_t rscm_b200_launch_count(const rscm_b200_ensemble *h) { return h ? h->launches : 0; }
+
+int64_t rscm_b200_shared_bytes(const rscm_b200_ensemble *h, int log_posterior) { return h ? static_cast<int64_t>(smem_bytes(h, log_posterior != 0)) : 0; }
 
 double rscm_b200_kernel_ms(rscm_b200_ensemble *h, int reset)
 {

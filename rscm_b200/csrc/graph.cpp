@@ -411,9 +411,12 @@ static const std::vector<KindInfo> &kinds()
          {0, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 0, 0,
           0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
           1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0},
-         48, /*n_state*/ 1, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10,
+         48, /*n_state*/ 2, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10,
          /*scratch_fixed*/ 0, /*no_slots*/ false, /*lanes*/ 1, /*aux_template*/ false,
-         /*n_smem_lanes: block-prefix sums of the convolution, one year of the block per role*/ 16, /*lane_aware*/ true, /*n_xch*/ 0},
+         /*n_smem_lanes: as one CTA-wide region, two staged history tiles (16 words x 128 threads = 2 x 32 months x 32
+           members); then, per thread, the block-prefix sums of the convolution (one word per month of the year:
+           smem_lanes_per_aux) — magicc_boxes.cuh*/ 16, /*lane_aware*/ true, /*n_xch: the tiles' two mbarriers*/ 1,
+         /*smem_lanes_per_aux*/ true},
     };
     static const bool extended = (k.push_back(halocarbon_kind()), true);
     (void)extended;
@@ -606,9 +609,16 @@ static void emit_program(Graph &g)
     int tmp_id = 0;
     // lane-group programs: role 0 (warp 0) runs the graph; lane nodes are entered by every role
     const bool lanes = g.lanes > 1;
+    // RSCM_B200_NODE_CLOCKS=1 (profiling aid, tools/node_clocks.py): thread 0 of CTA 0 accumulates the cycles it spends in each
+    // node and prints them after the last step.  The program text changes, so these builds have their own cache entries.
+    const bool node_clocks = std::getenv("RSCM_B200_NODE_CLOCKS") != nullptr;
+    if (node_clocks)
+        o << "        __shared__ long long node_clk[" << g.nodes.size() << "];\n        const bool clk_on = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;\n"
+             "        if (clk_on && cx.N == 0) for (int i = 0; i < " << g.nodes.size() << "; ++i) node_clk[i] = 0;\n        long long clk_t = 0;\n";
     for (int ni : g.order) {
         const Node &n = g.nodes[ni];
         const bool lane_node = lanes && n.kind != KIND_AGGREGATOR && n.lane_node;
+        if (node_clocks) o << "      clk_t = clock64();\n";
         o << "      " << (lanes && !lane_node ? "if (cx.role == 0) " : "") << "{ // node " << ni << "\n";
         std::ostringstream pre;
         if (n.kind == KIND_AGGREGATOR) {
@@ -723,6 +733,14 @@ static void emit_program(Graph &g)
             o << "        }\n";
             if (lane_node) o << "        }\n";
         }
+        o << "      }\n";
+        if (node_clocks) o << "      if (clk_on) node_clk[" << ni << "] += clock64() - clk_t;\n";
+    }
+    if (node_clocks) {
+        o << "      if (clk_on && cx.N == " << g.T - 2 << ") {\n";
+        for (int ni : g.order)
+            o << "        printf(\"node_clocks " << ni << " " << (g.nodes[ni].kind == KIND_AGGREGATOR ? "Aggregator" : kind_info(g.nodes[ni].kind)->dev_name)
+              << " %lld\\n\", node_clk[" << ni << "] / " << g.T - 1 << ");\n";
         o << "      }\n";
     }
     o << "    }\n";
@@ -987,13 +1005,15 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
             g.n_slots += static_cast<int>(n.params.size());
         }
         g.n_derived += k->n_derived;
+        if (k->aux_param >= 0) n.aux = static_cast<int>(n.params[k->aux_param]);
         // stateful kinds: per-thread state, shared-memory scratch, global scratch, per-graph constant tables
         n.state_base = g.n_state;
         n.smem_base = g.n_smem;
         n.scratch_base = g.n_scratch_rows;
         n.ctab_base = static_cast<int>(g.ctab.size());
         g.n_state += k->n_state;
-        g.n_smem += k->n_smem + (g.lanes > 1 ? k->n_smem_lanes : 0);
+        // (lane-group programs: n_smem_lanes fixed words, plus one per unit of the aux parameter for the kinds that say so)
+        g.n_smem += k->n_smem + (g.lanes > 1 ? k->n_smem_lanes + (k->smem_lanes_per_aux ? n.aux : 0) : 0);
         if (g.lanes > 1 && (k->lanes > 1 || k->lane_aware)) {
             // a lane node: its input values travel from role 0 to the other roles through the first exchange slots
             n.lane_node = true;
@@ -1031,7 +1051,6 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
             if (!terr.empty()) { err = terr; return false; }
             g.gtab.insert(g.gtab.end(), tab.begin(), tab.end());
         }
-        if (k->aux_param >= 0) n.aux = static_cast<int>(n.params[k->aux_param]);
         if (n.kind == RSCM_B200_N2O_CHEMISTRY && !(n.params[4] >= 0.0 && n.params[4] <= 6.0)) {
             err = "N2OChemistry: strat_delay must be in [0, 6] (history ring of the device kernel)";
             return false;

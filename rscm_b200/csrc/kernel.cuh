@@ -64,7 +64,11 @@ struct KArgs {
     const double *bounds; // [Tpad + 4] time bounds (T + 1 used), staged only for programs that need the time axis
     const double *ctab;   // [n_ctab] per-graph constant tables of stateful components (host-computed)
     const double *gtab;   // large per-graph tables that stay in global memory (e.g. the ocean IRF by lag)
-    double *scratch;      // [n_scratch][runs] member-interleaved global scratch of stateful components, or null
+    // global scratch of stateful components, or null: [S][ceil(M/32)][scratch_rows][32] — the rows of 32 consecutive
+    // members of one scenario are one contiguous block, so a warp's access to a row is one 256 B segment and a range of
+    // rows of a CTA's 32 members (lane-group programs) is one contiguous piece that a bulk copy can stage
+    double *scratch;
+    int scratch_rows;
     int n_ctab;
     int n_exo_rows, n_rk, n_obs_rows;
     int normalize;
@@ -97,45 +101,6 @@ struct KArgs {
 };
 
 static_assert(sizeof(KArgs) <= 32764, "kernel parameter block must stay within the launch limit (32764 B since CUDA 12.1, sm_70+)");
-
-// ---- mbarrier / TMA bulk-copy primitives (PTX) -----------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p)
-{
-    return static_cast<unsigned>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
 
 __device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
 
@@ -311,10 +276,8 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     cx.ctab = s_ctab;
     cx.gtab = a.gtab;
     cx.sm = s_thread;
-    cx.scratch = a.scratch ? a.scratch + run : nullptr;
-    cx.scratch0 = a.scratch;
-    cx.runs = a.runs;
-    cx.run = run;
+    cx.scratch = a.scratch ? a.scratch + ((static_cast<long long>(blockIdx.y) * ((a.M + 31) >> 5) + (m >> 5)) * a.scratch_rows) * SCR_LD + (m & 31) : nullptr;
+    cx.col = static_cast<int>(m & 31);
     cx.Tpad = a.Tpad;
     cx.N = 0;
     cx.role = role;

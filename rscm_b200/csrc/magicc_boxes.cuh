@@ -190,16 +190,30 @@ __device__ __forceinline__ bool n2o_chemistry_solve(const R *P, const R *, const
 //     blocks of four.  At the first year of a block role q sums the whole history that predates the block against the
 //     lags of the block's year q (12 prefix sums, kept in this thread's shared-memory column); role 0 then steps every
 //     year from the prefix sums of that year's role and adds the block's own months.  The long history is read once per
-//     FOUR years and by four warps at once (it is the HBM traffic that bounds the emissions-driven chain: 4200 months
-//     x 8 B per member at the end of a 350-year run); the accumulation order per month is unchanged (history before
-//     the block, then the block, oldest first).
-// P: see include/rscm_b200.h (60 values); S[0] = months of history so far.
+//     FOUR years and ONCE PER CTA: the rows of the CTA's 32 members are contiguous in the global scratch (KArgs::scratch),
+//     so tiles of OCEAN_KT months (8 KB) are staged in shared memory by bulk copies (cp.async.bulk + mbarrier, two tiles
+//     in flight) and the four warps read them from there — a quarter of the L2 traffic of four warps loading the same
+//     rows, and none of it through L1, which holds the spilled cells of these large programs.  The accumulation order
+//     per month is unchanged (history before the block, then the block, oldest first).
+// P: see include/rscm_b200.h (60 values); S[0] = months of history so far, S[1] = tiles staged so far (mbarrier phase).
+// Shared memory of the node in lane-group programs: as one CTA-wide region, words [0,16) x 128 threads are the two tiles
+// [2][OCEAN_KT][32]; then `steps` words per thread for the prefix sums.  The tiles' two mbarriers are the node's exchange slot.
+constexpr int OCEAN_KT = 32;
 template <class R> __device__ __forceinline__ void ocean_carbon_prepare(const R *P, R *D)
 {
     D[0] = P[3] / (P[4] * R(12));            // gas_exchange_rate
     D[1] = R(1.72e17) / (P[7] * P[8]);       // dic_conversion_factor
 }
-template <class R> __device__ __forceinline__ void ocean_carbon_init_state(const R *, const R *, R *S, const StepCtx<R> &, NodeRef) { S[0] = R(0); }
+template <class R> __device__ __forceinline__ void ocean_carbon_init_state(const R *, const R *, R *S, const StepCtx<R> &cx, NodeRef nr)
+{
+    S[0] = R(0);
+    S[1] = R(0);
+    if (cx.lanes == 4 && threadIdx.x == 0) {
+        unsigned long long *bars = reinterpret_cast<unsigned long long *>(cx.xch + nr.xch * 32); // (thread 0: lane 0's column = the slot's base)
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+    }
+}
 
 template <class R>
 __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R *out, const StepCtx<R> &cx, R *S, NodeRef nr)
@@ -213,18 +227,19 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     const R k_gas = D[0], dic_conv = D[1];
     const int n_old = static_cast<int>(S[0]);
     const double *irf = cx.gtab + nr.gt;
-    double *hist = cx.scratch + static_cast<long long>(nr.scr) * cx.runs;
+    double *hist = cx.scratch + static_cast<long long>(nr.scr) * SCR_LD;
     R acc[MAXS];
-    // sum over history entries [i0, i1) against the lags of months `first_month + m` (m < steps), oldest entry first.
-    // Chunks of 16 months: sixteen independent (coalesced, member-interleaved) flux loads in flight, and the IRF lags of a
-    // chunk form one sliding window of 15 + steps values (uniform loads) instead of steps loads per month.
-    auto convolve = [&](int i0, int i1, int first_month) {
+    // sum over history entries [i0, i1) (entry i at src[i * SCR_LD]: the global scratch, or a staged tile, which has the
+    // same row length) against the lags of months `first_month + m` (m < steps), oldest entry first.  Chunks of 16 months:
+    // sixteen independent loads in flight, and the IRF lags of a chunk form one sliding window of 15 + steps values
+    // (uniform loads) instead of steps loads per month.
+    auto convolve = [&](const double *src, int i0, int i1, int first_month) {
         constexpr int CH = 16;
         int i = i0;
         for (; i + CH <= i1; i += CH) {
             R f[CH];
 #pragma unroll
-            for (int u = 0; u < CH; ++u) f[u] = R(hist[static_cast<long long>(i + u) * cx.runs]);
+            for (int u = 0; u < CH; ++u) f[u] = R(src[(i + u) * SCR_LD]);
             const double *wb = irf + (first_month - i - (CH - 1)); // wb[k]: lag first_month - i - (CH - 1) + k
             R wv[CH - 1 + MAXS];
 #pragma unroll
@@ -237,7 +252,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
                     if (m < steps) acc[m] += f[u] * wv[(CH - 1 - u) + m];
         }
         for (; i < i1; ++i) {
-            const R f = R(hist[static_cast<long long>(i) * cx.runs]);
+            const R f = R(src[i * SCR_LD]);
             const double *w = irf + (first_month - i);
 #pragma unroll
             for (int m = 0; m < MAXS; ++m)
@@ -246,15 +261,39 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     };
     // a flux older than max_history_months has left the reference's deque: no need to load it (its weights are zero)
     const int max_hist = static_cast<int>(P[11]);
+    auto oldest = [&](int first_month) { const int lo = first_month + 1 - max_hist; return lo > 0 ? (lo < n_old ? lo : n_old) : 0; };
     if (cx.lanes == 4) {
-        R *A = cx.sm + nr.sm * BLOCK * (8 / static_cast<int>(sizeof(R))); // this thread's prefix sums, month m at A[m * BLOCK]
+        R *A = cx.sm + (nr.sm + 16) * BLOCK * (8 / static_cast<int>(sizeof(R))); // this thread's prefix sums, month m at A[m * BLOCK]
         const int yb = (n_old / steps) & 3;                               // year within the block of four (CTA-uniform)
         if (yb == 0) {
             const int first_month = n_old + steps * cx.role;              // role q prepares year q of the block
 #pragma unroll
             for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
-            const int lo = first_month + 1 - max_hist;
-            convolve(lo > 0 ? (lo < n_old ? lo : n_old) : 0, n_old, first_month);
+            double *cta = reinterpret_cast<double *>(cx.sm - threadIdx.x);
+            double *tiles = cta + nr.sm * BLOCK;
+            unsigned long long *bars = reinterpret_cast<unsigned long long *>(cx.xch - (threadIdx.x & 31) + nr.xch * 32);
+            const int lo_cta = oldest(n_old), lo_role = oldest(first_month); // role 0 reaches furthest back
+            const int nt = (n_old - lo_cta + OCEAN_KT - 1) / OCEAN_KT;
+            const int tc = static_cast<int>(S[1]);
+            auto stage = [&](int t) { // thread 0 (lane 0 of the CTA's block: its `hist` is the block's row base)
+                const int ts = lo_cta + t * OCEAN_KT;
+                const unsigned bytes = static_cast<unsigned>((n_old - ts < OCEAN_KT ? n_old - ts : OCEAN_KT) * SCR_LD * 8);
+                void *bar = bars + ((tc + t) & 1);
+                mbar_expect_tx(bar, bytes);
+                tma_bulk_g2s(tiles + ((tc + t) & 1) * OCEAN_KT * SCR_LD, hist + static_cast<long long>(ts) * SCR_LD, bytes, bar);
+            };
+            if (threadIdx.x == 0) {
+                if (nt > 0) stage(0);
+                if (nt > 1) stage(1);
+            }
+            for (int t = 0; t < nt; ++t) {
+                const int k = tc + t, ts = lo_cta + t * OCEAN_KT, te = ts + OCEAN_KT < n_old ? ts + OCEAN_KT : n_old;
+                mbar_wait(bars + (k & 1), (k >> 1) & 1);
+                convolve(tiles + (k & 1) * OCEAN_KT * SCR_LD + cx.col - ts * SCR_LD, ts > lo_role ? ts : lo_role, te, first_month);
+                __syncthreads(); // every warp is done with this tile: its buffer can take the tile after next
+                if (threadIdx.x == 0 && t + 2 < nt) stage(t + 2);
+            }
+            S[1] = R(tc + nt);
 #pragma unroll
             for (int m = 0; m < MAXS; ++m)
                 if (m < steps) A[m * BLOCK] = acc[m];
@@ -268,12 +307,11 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
         const R *Ay = A + ((((yb - cx.rot) & 3) - ((-cx.rot) & 3)) * 32);
 #pragma unroll
         for (int m = 0; m < MAXS; ++m) acc[m] = (m < steps) ? Ay[m * BLOCK] : R(0);
-        convolve(n_old - yb * steps, n_old, n_old); // the block's own months so far (just written: L1 / L2 resident)
+        convolve(hist, n_old - yb * steps, n_old, n_old); // the block's own months so far (just written: L1 / L2 resident)
     } else {
 #pragma unroll
         for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
-        const int lo = n_old + 1 - max_hist;
-        convolve(lo > 0 ? (lo < n_old ? lo : n_old) : 0, n_old, n_old);
+        convolve(hist, oldest(n_old), n_old, n_old);
     }
     R fy[MAXS];
     R total_flux = R(0);
@@ -282,7 +320,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     for (int m = 0; m < MAXS; ++m) {
         if (m < steps) {
             const R flux_ppm = k_gas * (co2 - pco2);
-            if (cx.live) hist[static_cast<long long>(n_old + m) * cx.runs] = static_cast<double>(flux_ppm);
+            if (cx.live) hist[(n_old + m) * SCR_LD] = static_cast<double>(flux_ppm);
             fy[m] = flux_ppm;
             const R flux_gtc_yr = flux_ppm * R(12) * R(2.124);
             total_flux += flux_gtc_yr / R(steps);
@@ -300,6 +338,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
             pco2 = (P[2] + dp) * tfac;
         }
     }
+    if (cx.lanes == 4) fence_proxy_async(); // the months just written are staged by bulk copies from the next block of years on
     S[0] = R(n_old + steps);
     out[0] = total_flux;
     out[1] = pco2;
