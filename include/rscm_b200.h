@@ -326,8 +326,9 @@ int rscm_b200_measure_fma_peak(int device, int dtype, double *tflops);
 int rscm_b200_interpolate_device(const double *d_src_times, int64_t K, const double *d_src_values, int64_t n_series, int R,
                                  const double *d_dst_times, int64_t T, int strategy, double *d_out, void *stream);
 
-/* Self-test hook: y[i] = exp(x[i]) (op 0) or log(x[i]) (op 1) with the engine's own fp64 device implementations
- * (constant-bank coefficients; rscm_b200/csrc/components.cuh), so that their accuracy can be checked from the host. */
+/* Self-test hook: y[i] = exp(x[i]) (op 0), log(x[i]) (op 1) or pow(x[2i], x[2i+1]) (op 2; x holds 2n values) with the
+ * engine's own fp64 device implementations (rscm_b200/csrc/components.cuh), so that their accuracy can be checked
+ * from the host.  n = number of results. */
 int rscm_b200_device_math(int op, const double *d_x, int64_t n, double *d_y, void *stream);
 
 /* ---- ensemble sampler: the stretch move on the device ------------------------

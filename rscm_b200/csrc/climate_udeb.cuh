@@ -388,6 +388,14 @@ __device__ __forceinline__ void udeb_substep(const UdebYear<R> &y, const R *P, c
     }
 }
 
+// RSCM_NODE_CLOCKS (profiling aid, set by the JIT when RSCM_B200_NODE_CLOCKS is in the environment): thread 0 of CTA 0
+// accumulates the cycles of the phases of a model year and prints the averages after the last step.
+#ifdef RSCM_NODE_CLOCKS
+#define UDEB_CLK(i) do { if (clk_on) { const long long now_ = clock64(); udeb_clk[i] += now_ - clk_t; clk_t = now_; } } while (0)
+#else
+#define UDEB_CLK(i) do { } while (0)
+#endif
+
 // in: [ERF at_start, ERF at_end, Surface Temperature[4] at_start]
 // out: [Heat Uptake, Ocean Heat Content, Sea Surface Temperature, Surface Temperature[4]]
 template <class R, int N>
@@ -398,6 +406,12 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     const bool ok = S[US_OK] != R(0);
     const int steps_n = static_cast<int>(P[U_STEPS]);
     const int q = cx.role, h = q & 1;
+#ifdef RSCM_NODE_CLOCKS
+    __shared__ long long udeb_clk[8];
+    const bool clk_on = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    if (clk_on && cx.N == 0) for (int i = 0; i < 8; ++i) udeb_clk[i] = 0;
+    long long clk_t = clock64();
+#endif
     const bool bottom = (q & 2) != 0;
     constexpr int K = (N - 2) >> 1, NT = K + 1, NB = N - K - 1;
     R *T = S + US_T;
@@ -439,6 +453,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         if (q == 0) X[UX_T0 * 32] = static_cast<double>(T[0]); // the NH mixed-layer temperature (warm-start test below)
     }
     __syncthreads();
+    UDEB_CLK(0); // history sums + barrier
     // Role 0 alone turns the history into this year's feedback parameters (LAMCALC: up to 40 secant iterations) and
     // publishes them; the other warps wait at the barrier.
     if (q == 0) {
@@ -457,6 +472,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         X[(UX_LAM + 1) * 32] = static_cast<double>(ll);
         X[(UX_LAM + 2) * 32] = static_cast<double>(ef);
     }
+    UDEB_CLK(1); // LAMCALC (role 0)
     __syncthreads();
     const R lam_o = R(X[UX_LAM * 32]), lam_l = R(X[(UX_LAM + 1) * 32]), co2_eff = R(X[(UX_LAM + 2) * 32]);
     if (R(X[UX_T0 * 32]) == R(0) && in[2] != R(0)) { // warm start from non-zero initial surface temperatures (mod.rs:439-448)
@@ -514,6 +530,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     const R wmin_b = (wmin == wmin) ? wmin : -R(RSCM_INF_F);
     const R inv_wt_nh = R(1) / P[U_WT_NH], inv_wt_sh = R(1) / P[U_WT_SH];
     R sst_nh = R(0), sst_sh = R(0);
+    UDEB_CLK(2); // the year's constants
     for (int step = 1; step <= steps_n; ++step) {
         const R frac = R(step) * inv_steps;
         const R erf = erf_start + frac * (erf_end - erf_start);
@@ -523,10 +540,12 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
             if (!(fgsl < R(1e-15))) S[US_GR1] += gr_c1 * (S[US_LAND1] - S[US_GR1]);
         }
         udeb_substep<R, N>(y, P, S, tab, q, X, T, F, e * (h ? S[US_QF2] : S[US_QF0]));
+        UDEB_CLK(3); // sweeps, rendezvous, back substitution
         // one rendezvous serves two purposes: the new sea-surface temperatures for the land / upwelling updates below,
         // and the edge temperatures (mixed layer, bottom layer) the next sub-step's sweeps start from
         X[(UX_EDGE + q) * 32] = static_cast<double>(T[0]);
         __syncthreads();
+        UDEB_CLK(4); // edge rendezvous
         sst_nh = R(X[UX_EDGE * 32]);
         sst_sh = R(X[(UX_EDGE + 1) * 32]);
         const R air_nho = udeb_sst_to_air(air, sst_nh), air_sho = udeb_sst_to_air(air, sst_sh);
@@ -538,6 +557,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         const R gt = air_nho * fgno + S[US_LAND0] * fgnl + air_sho * fgso + S[US_LAND1] * fgsl;
         S[US_W0] = udeb_floor(w0 * (R(1) - fv * udeb_cap(gt * inv_wt_nh, R(1))), wmin_b);
         S[US_W1] = udeb_floor(w0 * (R(1) - fv * udeb_cap(gt * inv_wt_sh, R(1))), wmin_b);
+        UDEB_CLK(5); // land boxes, upwelling
     }
     S[US_AE0] = (r_abs(sst_nh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(air, sst_nh) / sst_nh;
     S[US_AE1] = (r_abs(sst_sh) < R(1e-15)) ? P[U_TA_ALPHA] : udeb_sst_to_air(air, sst_sh) / sst_sh;
@@ -570,6 +590,13 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
     }
     out[2] = (sst_nh + sst_sh) / R(2);
     for (int i = 0; i < 4; ++i) out[3 + i] = st[i];
+    UDEB_CLK(6); // outputs, heat content
+#ifdef RSCM_NODE_CLOCKS
+    if (clk_on && cx.N == cx.n_steps - 1)
+        printf("udeb_clocks hist %lld lamcalc %lld constants %lld sweeps %lld edge_barrier %lld land %lld outputs %lld (cycles per year)\n",
+               udeb_clk[0] / cx.n_steps, udeb_clk[1] / cx.n_steps, udeb_clk[2] / cx.n_steps, udeb_clk[3] / cx.n_steps,
+               udeb_clk[4] / cx.n_steps, udeb_clk[5] / cx.n_steps, udeb_clk[6] / cx.n_steps);
+#endif
     return ok;
 }
 

@@ -60,6 +60,19 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
         "r"(parity)
         : "memory");
 }
+// The same copy with an L2 evict-first policy: for data that streams through once per pass and is far larger than L2 (the
+// flux history of OceanCarbon), so that it does not push out the lines that are re-used (the spilled cells of the large
+// programs live in local memory, i.e. in L2).
+__device__ __forceinline__ void tma_bulk_g2s_stream(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 // Global memory written with ordinary stores and later read by a bulk copy (the async proxy): the writer fences, then
 // synchronises with the thread that issues the copy.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -75,6 +88,7 @@ template <class R> struct StepCtx {
     int col;              // this run's column in its block of the global scratch (= member & 31)
     int Tpad;
     int N;                // current time index
+    int n_steps;          // steps of the run (T - 1)
     // Lane groups (Prog::LANES == 4: programs with ClimateUDEB).  Each warp of the CTA is one ROLE of the CTA's 32
     // members: lane l of every warp belongs to member l.  Role 0 runs the component graph thread-per-member; the kinds
     // that spread a member over four threads (ClimateUDEB's half-sweeps, OceanCarbon's history sums) are entered by all
@@ -181,9 +195,45 @@ template <class R> __device__ __forceinline__ R r_sqrt(R x);
 template <> __device__ __forceinline__ double r_sqrt<double>(double x) { return sqrt(x); }
 template <> __device__ __forceinline__ float r_sqrt<float>(float x) { return sqrtf(x); }
 template <class R> __device__ __forceinline__ R r_pow(R x, R y);
-// pow() inlines to a few hundred instructions per call site; the MAGICC chain has fourteen of them per model year, half of
-// its per-year code, which is already far larger than the instruction cache: one out-of-line copy instead
-__device__ __noinline__ double rscm_pow(double x, double y) { return pow(x, y); }
+// pow.  The library version is about three hundred instructions per call; the MAGICC chain makes fourteen calls per model
+// year (the Prather iterations of CH4 / N2O, the CH4-N2O overlap terms, stratospheric ozone), most of them one after the
+// other.  x^y = exp(y log x) from the tables above: log x is kept as an unevaluated sum hi + lo (the table's high part
+// plus e ln2 with their rounding error recovered; everything else in lo: absolute error about 2^-61), y (hi + lo) likewise,
+// and the part of the exponent that rounding to a double drops is applied to the result, e^(s + sl) = e^s (1 + sl).  About
+// 1 ulp (tests/test_device_math.py: <= 2 ulp against the host library).  Zero, negative, subnormal, infinite or NaN x, a
+// non-finite y and |y log x| >= 700 go to the library function.  One out-of-line copy: these programs are far larger than
+// the instruction cache.
+__device__ __noinline__ double rscm_pow_slow(double x, double y) { return pow(x, y); }
+__device__ __noinline__ double rscm_pow(double x, double y)
+{
+    int hx = __double2hiint(x);
+    if (static_cast<unsigned>(hx - 0x00100000) >= 0x7fe00000u || (__double2hiint(y) & 0x7fffffff) >= 0x7ff00000) return rscm_pow_slow(x, y);
+    int e = (hx >> 20) - 1023;
+    hx = (hx & 0x000fffff) | 0x3ff00000;
+    if (hx >= 0x3ff6a09f) { hx -= 0x00100000; e += 1; } // m in [sqrt(1/2), sqrt(2))
+    const double m = __hiloint2double(hx, __double2loint(x));
+    const int j = __double2loint(fma(m, 256.0, 6755399441055744.0)) - RSCM_LOG_J0;
+    const double2 t01 = __ldg(reinterpret_cast<const double2 *>(RSCM_LOG_TAB[j]));
+    const double2 t23 = __ldg(reinterpret_cast<const double2 *>(RSCM_LOG_TAB[j]) + 1);
+    const double u = (m - t01.x) * t01.y;
+    double p = fma(u, RSCM_LOG_C[6], RSCM_LOG_C[5]);
+    p = fma(u, p, RSCM_LOG_C[4]);
+    p = fma(u, p, RSCM_LOG_C[3]);
+    p = fma(u, p, RSCM_LOG_C[2]);
+    const double r = fma(u * u, p, u);
+    const double ed = static_cast<double>(e);
+    const double a = ed * RSCM_LOG_C[0];                // exact: 11 bits x 31 bits
+    const double hi = a + t23.x;
+    const double bb = hi - a;
+    const double lo = ((a - (hi - bb)) + (t23.x - bb)) + (r + fma(ed, RSCM_LOG_C[1], t23.y));
+    const double ph = y * hi;
+    const double pl = fma(y, hi, -ph) + y * lo;
+    const double sh = ph + pl;
+    if (!(fabs(sh) < 700.0)) return rscm_pow_slow(x, y);
+    const double sl = (ph - sh) + pl;
+    const double ex = rscm_exp(sh);
+    return fma(ex, sl, ex);
+}
 template <> __device__ __forceinline__ double r_pow<double>(double x, double y) { return rscm_pow(x, y); }
 template <> __device__ __forceinline__ float r_pow<float>(float x, float y) { return powf(x, y); }
 template <class R> __device__ __forceinline__ R r_nan();
@@ -363,9 +413,17 @@ __device__ __forceinline__ bool co2_erf_solve(const R *P, const R *D, const R *i
 //   P: see include/rscm_b200.h (21 values, method first)
 // ---------------------------------------------------------------------------
 constexpr int GHG_FORCING_NP = 21;
-constexpr int GHG_FORCING_ND = 1;
+constexpr int GHG_FORCING_ND = 3;
 
-template <class R> __device__ __forceinline__ void ghg_forcing_prepare(const R *, R *D) { D[0] = R(0); }
+template <class R> __device__ __forceinline__ R ghg_overlap_f(R ch4, R n2o);
+// D: the terms of the pre-industrial concentrations, which every step subtracts: overlap(ch4_pi, n2o_pi) (Ipcctar only:
+// two pow and a log), sqrt(ch4_pi), sqrt(n2o_pi)
+template <class R> __device__ __forceinline__ void ghg_forcing_prepare(const R *P, R *D)
+{
+    D[0] = (P[0] == R(0)) ? ghg_overlap_f<R>(P[2], P[3]) : R(0);
+    D[1] = r_sqrt<R>(P[2]);
+    D[2] = r_sqrt<R>(P[3]);
+}
 
 template <class R> __device__ __forceinline__ R ghg_overlap_f(R ch4, R n2o)
 {
@@ -375,16 +433,14 @@ template <class R> __device__ __forceinline__ R ghg_overlap_f(R ch4, R n2o)
 }
 
 template <class R>
-__device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
+__device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *D, const R *in, R *out, const StepCtx<R> &, R *, NodeRef)
 {
     const R co2 = in[0], ch4 = in[1], n2o = in[2];
     R co2_raw, ch4_raw, n2o_raw;
     if (P[0] == R(0)) { // Ipcctar, ghg.rs:164-200
         co2_raw = (P[4] / R(0.6931471805599453094172321)) * r_log_call<R>(co2 / P[1]);
-        ch4_raw = P[5] * (r_sqrt<R>(ch4) - r_sqrt<R>(P[2])) -
-                  (ghg_overlap_f<R>(ch4, P[3]) - ghg_overlap_f<R>(P[2], P[3]));
-        n2o_raw = P[6] * (r_sqrt<R>(n2o) - r_sqrt<R>(P[3])) -
-                  (ghg_overlap_f<R>(P[2], n2o) - ghg_overlap_f<R>(P[2], P[3]));
+        ch4_raw = P[5] * (r_sqrt<R>(ch4) - D[1]) - (ghg_overlap_f<R>(ch4, P[3]) - D[0]);
+        n2o_raw = P[6] * (r_sqrt<R>(n2o) - D[2]) - (ghg_overlap_f<R>(P[2], n2o) - D[0]);
     } else { // Olbl, ghg.rs:205-259
         const R co2_pi = P[1], a1 = P[7], b1 = P[8], c1 = P[9], d1 = P[10];
         const R delta = co2 - co2_pi;
@@ -396,8 +452,8 @@ __device__ __forceinline__ bool ghg_forcing_solve(const R *P, const R *, const R
         else alpha = a1 * delta * delta + b1 * delta + d1 + n2o_overlap;
         co2_raw = alpha * r_log_call<R>(co2 / co2_pi);
         const R s_ch4 = r_sqrt<R>(ch4), s_n2o = r_sqrt<R>(n2o), s_co2 = r_sqrt<R>(co2);
-        ch4_raw = (P[11] * s_ch4 + P[12] * s_n2o + P[13]) * (s_ch4 - r_sqrt<R>(P[2]));
-        n2o_raw = (P[14] * s_co2 + P[15] * s_n2o + P[16] * s_ch4 + P[17]) * (s_n2o - r_sqrt<R>(P[3]));
+        ch4_raw = (P[11] * s_ch4 + P[12] * s_n2o + P[13]) * (s_ch4 - D[1]);
+        n2o_raw = (P[14] * s_co2 + P[15] * s_n2o + P[16] * s_ch4 + P[17]) * (s_n2o - D[2]);
     }
     out[0] = co2_raw * P[18];
     out[1] = ch4_raw * P[19];

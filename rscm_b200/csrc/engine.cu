@@ -997,7 +997,7 @@ int rscm_b200_interpolate_device(const double *d_src_times, int64_t K, const dou
 int rscm_b200_device_math(int op, const double *d_x, int64_t n, double *d_y, void *stream)
 {
     rscm_b200_ensemble *h = nullptr;
-    if ((op != 0 && op != 1) || !d_x || !d_y || n < 0) return fail(nullptr, RSCM_B200_EINVAL, "device_math: bad argument");
+    if (op < 0 || op > 2 || !d_x || !d_y || n < 0) return fail(nullptr, RSCM_B200_EINVAL, "device_math: bad argument");
     if (n == 0) return RSCM_B200_OK;
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 148 * 8));
     rscm_dev::device_math_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(op, d_x, n, d_y);

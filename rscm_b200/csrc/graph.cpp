@@ -271,7 +271,7 @@ static const std::vector<KindInfo> &kinds()
           "olbl_co2_a1", "olbl_co2_b1", "olbl_co2_c1", "olbl_co2_d1", "olbl_ch4_a3", "olbl_ch4_b3",
           "olbl_ch4_d3", "olbl_n2o_a2", "olbl_n2o_b2", "olbl_n2o_c2", "olbl_n2o_d2", "adjust_co2",
           "adjust_ch4", "adjust_n2o"},
-         1, -2, {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 40},
+         3, -2, {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 40},
         {RSCM_B200_OZONE_FORCING, "OzoneForcing", "ozone_forcing",
          // crates/rscm-magicc/src/forcing/ozone.rs (derive block)
          {{"EESC", REQ_INPUT, RSCM_B200_SCALAR},
@@ -540,6 +540,9 @@ static void emit_program(Graph &g)
     o << "    static constexpr int NSM = " << g.n_smem << ";\n";
     o << "    static constexpr int LANES = " << g.lanes << ";\n";
     o << "    static constexpr int NXCH = " << g.n_xch << ";\n";
+    // more cells than a thread can keep in registers next to its working set: they live in local memory, and the kernel
+    // swaps the two time levels instead of copying them (kernel.cuh)
+    o << "    static constexpr bool SWAP_CELLS = " << (g.n_cells > 64 ? "true" : "false") << ";\n";
     o << "    static constexpr bool SYNC_STEPS = " << (g.n_cells > 64 ? "true" : "false") << ";\n";
     o << "    static constexpr bool NEEDS_TIME = " << (g.needs_time ? "true" : "false") << ";\n";
     // exogenous rows are staged into shared memory unless per-thread scratch or a long row list needs the space
@@ -695,10 +698,22 @@ static void emit_program(Graph &g)
                 o << "        if (cx.role == 0) {\n        if (ok) {\n";
             } else {
             o << pre.str();
-            o << "        const R in[" << (in_exprs.empty() ? 1 : in_exprs.size()) << "] = {";
-            for (size_t i = 0; i < in_exprs.size(); ++i) o << (i ? ", " : "") << in_exprs[i];
-            if (in_exprs.empty()) o << "R(0)";
-            o << "};\n";
+            // inputs that are a run of consecutive current-level cells (HalocarbonChemistry's 82 in a schema that lists a
+            // species' emissions and concentration together) are read in place: no copy of cells that live in local memory
+            int run0 = -1;
+            if (in_exprs.size() >= 8 && in_exprs[0].rfind("cur[", 0) == 0) {
+                run0 = std::atoi(in_exprs[0].c_str() + 4);
+                for (size_t i = 0; i < in_exprs.size() && run0 >= 0; ++i)
+                    if (in_exprs[i] != "cur[" + std::to_string(run0 + static_cast<int>(i)) + "]") run0 = -1;
+            }
+            if (run0 >= 0) {
+                o << "        const R *in = cur + " << run0 << ";\n";
+            } else {
+                o << "        const R in[" << (in_exprs.empty() ? 1 : in_exprs.size()) << "] = {";
+                for (size_t i = 0; i < in_exprs.size(); ++i) o << (i ? ", " : "") << in_exprs[i];
+                if (in_exprs.empty()) o << "R(0)";
+                o << "};\n";
+            }
             o << "        R out[" << n_out_vals << "];\n";
             o << "        if (" << solve_call << ") {\n";
             }

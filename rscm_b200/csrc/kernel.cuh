@@ -133,7 +133,7 @@ __device__ inline double prior_ln_pdf(const PriorDev &p, double x)
 // GaussianLikelihood::observation_ln_likelihood — likelihood.rs:186-199
 template <class R, int NC>
 __device__ __forceinline__ void obs_accumulate(const KArgs &a, const double *s_obs, int tidx,
-                                               const R (&vals)[NC], double (&ll)[MAX_OBS_ROWS], bool &bad)
+                                               const R *vals, double (&ll)[MAX_OBS_ROWS], bool &bad)
 {
 #pragma unroll
     for (int j = 0; j < MAX_OBS_ROWS; ++j) {
@@ -251,7 +251,13 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
         for (int j = 0; j < a.n_cols; ++j) lp += prior_ln_pdf(a.priors[j], __ldg(pm + j * a.ld_col));
     }
 
-    R cur[NC], nxt[NC];
+    // The cells of the two time levels.  Small programs keep them in registers and copy next -> current after every step
+    // (register moves the compiler folds away); the large MAGICC programs spill them to local memory, where that copy
+    // would be two memory operations per cell and step: Prog::SWAP_CELLS exchanges the two pointers instead.
+    R cells0[NC], cells1[NC];
+    R *cur = cells0, *nxt = cells1;
+    // lane-group programs: only role 0 runs the component graph and owns cells
+    const bool cells_on = LANES == 1 || role == 0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         cur[c] = a.init_col[c] >= 0 ? static_cast<R>(__ldg(pm + a.init_col[c] * a.ld_col)) : static_cast<R>(a.init_def[c]);
@@ -280,6 +286,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     cx.col = static_cast<int>(m & 31);
     cx.Tpad = a.Tpad;
     cx.N = 0;
+    cx.n_steps = a.T - 1;
     cx.role = role;
     cx.lanes = LANES;
     cx.live = active;
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
             tnext += a.t_step;
         }
     }
-    if (LOGP) obs_accumulate<R, NC>(a, s_obs, 0, cur, ll, bad);
+    if (LOGP && cells_on) obs_accumulate<R, NC>(a, s_obs, 0, cur, ll, bad);
 
     const int T = a.T;
     for (int N = 0; N < T - 1; ++N) {
@@ -320,10 +327,12 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
         // model year) keep the warps of a CTA in step, so that they fetch the same instructions together instead of
         // streaming four copies.  (Padding threads have exited or skip the step; a barrier counts non-exited threads.)
         if (Prog::SYNC_STEPS && LANES == 1) __syncthreads();
+        if (cells_on) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(x_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
-            else if (Prog::nan_init(c)) nxt[c] = r_nan<R>(); // other cells are overwritten on every path of the step
+            for (int c = 0; c < NC; ++c) {
+                if (Prog::exo_row(c) >= 0) nxt[c] = static_cast<R>(x_exo[Prog::exo_row(c) * a.Tpad + N + 1]);
+                else if (Prog::nan_init(c)) nxt[c] = r_nan<R>(); // other cells are overwritten on every path of the step
+            }
         }
         cx.N = N;
         if (LANES > 1 || !LOGP || active) Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
@@ -341,9 +350,13 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
                 tnext += a.t_step;
             }
         }
-        if (LOGP) obs_accumulate<R, NC>(a, s_obs, N + 1, nxt, ll, bad);
+        if (LOGP && cells_on) obs_accumulate<R, NC>(a, s_obs, N + 1, nxt, ll, bad);
+        if (Prog::SWAP_CELLS) {
+            R *t = cur; cur = nxt; nxt = t;
+        } else if (cells_on) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) cur[c] = nxt[c];
+            for (int c = 0; c < NC; ++c) cur[c] = nxt[c];
+        }
     }
 
     if (a.status && writer) {
@@ -573,7 +586,7 @@ __global__ void interpolate_kernel(const double *__restrict__ src_t, long long K
 __global__ void device_math_kernel(int op, const double *__restrict__ x, long long n, double *__restrict__ y)
 {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
-        y[i] = op == 0 ? rscm_exp(x[i]) : rscm_log(x[i]);
+        y[i] = op == 0 ? rscm_exp(x[i]) : op == 1 ? rscm_log(x[i]) : rscm_pow(x[2 * i], x[2 * i + 1]);
 }
 
 // FMA-pipe saturating micro-benchmark (roofline denominator for the FP64/FP32 bound)

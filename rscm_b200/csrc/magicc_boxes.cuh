@@ -280,7 +280,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
                 const unsigned bytes = static_cast<unsigned>((n_old - ts < OCEAN_KT ? n_old - ts : OCEAN_KT) * SCR_LD * 8);
                 void *bar = bars + ((tc + t) & 1);
                 mbar_expect_tx(bar, bytes);
-                tma_bulk_g2s(tiles + ((tc + t) & 1) * OCEAN_KT * SCR_LD, hist + static_cast<long long>(ts) * SCR_LD, bytes, bar);
+                tma_bulk_g2s_stream(tiles + ((tc + t) & 1) * OCEAN_KT * SCR_LD, hist + static_cast<long long>(ts) * SCR_LD, bytes, bar);
             };
             if (threadIdx.x == 0) {
                 if (nt > 0) stage(0);
@@ -320,7 +320,7 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     for (int m = 0; m < MAXS; ++m) {
         if (m < steps) {
             const R flux_ppm = k_gas * (co2 - pco2);
-            if (cx.live) hist[(n_old + m) * SCR_LD] = static_cast<double>(flux_ppm);
+            if (cx.live) __stcs(hist + (n_old + m) * SCR_LD, static_cast<double>(flux_ppm)); // streaming: next read in 1..4 years, after ~1 GB of other traffic
             fy[m] = flux_ppm;
             const R flux_gtc_yr = flux_ppm * R(12) * R(2.124);
             total_flux += flux_gtc_yr / R(steps);
@@ -376,8 +376,9 @@ __device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R 
     // on a uniform time axis the decay factors are constants of the graph (host-computed, graph.cpp)
     const bool uniform_dt = static_cast<double>(dt) == tab[HALO_CT * HALO_NS];
     // One ROLLED loop over the 41 species: unrolled it is 3.5 k instructions of a program that is bound by instruction
-    // fetch.  The dynamic indices put in / out / S of this component into local memory (L1-resident: 4 doubles per species).
-#pragma unroll 1
+    // fetch.  The dynamic indices put in / out / S of this component into local memory, which in these programs is served
+    // by L2 (shared memory takes most of the SM's L1): four species per trip keep four sets of loads in flight.
+#pragma unroll 4
     for (int s = 0; s < HALO_NS; ++s) {
         const double *t = tab + HALO_CT * s;
         const R lifetime = R(t[0]), conv = R(t[1]), rad_eff = R(t[2]), conc_pi = R(t[3]), loading = R(t[4]), release = R(t[5]);

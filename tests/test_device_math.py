@@ -1,4 +1,4 @@
-"""The engine's own fp64 exp / log (rscm_b200/csrc/components.cuh: constant-bank coefficients, table-driven exp) against
+"""The engine's own fp64 exp / log / pow (rscm_b200/csrc/components.cuh: constant-bank coefficients, table-driven exp) against
 the host library over the ranges the components use and over the special cases that take the library fall-back."""
 
 import numpy as np
@@ -10,8 +10,8 @@ from rscm_b200 import _ffi
 def device(op, x):
     import torch
     d_x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
-    d_y = torch.empty_like(d_x)
-    _ffi.check(_ffi.lib.rscm_b200_device_math(op, d_x.data_ptr(), d_x.numel(), d_y.data_ptr(), None))
+    d_y = torch.empty(d_x.shape[0], dtype=torch.float64, device="cuda")     # op 2 (pow): x is [n][2] = (base, exponent)
+    _ffi.check(_ffi.lib.rscm_b200_device_math(op, d_x.data_ptr(), d_y.numel(), d_y.data_ptr(), None))
     torch.cuda.synchronize()
     return d_y.cpu().numpy()
 
@@ -53,3 +53,27 @@ def test_log_within_one_ulp_and_special_cases():
     assert np.array_equal(np.isnan(gs), np.isnan(ws))
     ok = ~np.isnan(ws)
     assert np.all((gs[ok] == ws[ok]) | (ulp_error(gs[ok], ws[ok]) <= 1.0))
+
+
+@pytest.mark.gpu
+def test_pow_within_two_ulp_and_special_cases():
+    rng = np.random.default_rng(3)
+    # the components' ranges: burden ratios >= 1 with lifetime exponents, the CH4 x N2O products of the overlap terms
+    # (1e5 .. 1e7 ppb^2, exponents 0.75 and 1.52), EESC ratios with the chlorine exponent; then a wide sweep
+    base = np.concatenate([rng.uniform(1.0, 12.0, 300_000), rng.uniform(1e4, 1e8, 200_000), rng.uniform(1e-3, 1.0, 100_000),
+                           np.exp(rng.uniform(-300.0, 300.0, 200_000)), 1.0 + rng.uniform(-1e-6, 1e-6, 50_000)])
+    expo = np.concatenate([rng.uniform(-1.0, 2.0, 300_000), rng.choice([0.75, 1.52], 200_000), rng.uniform(0.5, 2.5, 100_000),
+                           rng.uniform(-2.0, 2.0, 200_000), rng.uniform(-50.0, 50.0, 50_000)])
+    got, want = device(2, np.stack([base, expo], axis=1)), np.power(base, expo)
+    assert np.max(ulp_error(got, want)) <= 2.0
+    # exact cases and the library fall-back
+    sp = np.array([[1.0, 3.7], [5.0, 0.0], [np.nan, 0.0], [2.0, 10.0], [4.0, 0.5], [0.0, 2.0], [0.0, -1.0], [-8.0, 3.0], [-8.0, 0.5],
+                   [np.inf, 2.0], [np.inf, -2.0], [3.0, np.inf], [0.5, np.inf], [3.0, np.nan], [1e300, 5.0], [1e-300, 5.0],
+                   [5e-324, 0.5], [10.0, 308.0], [10.0, -320.0], [2.0, 1023.0]])
+    with np.errstate(all="ignore"):
+        ws = np.power(sp[:, 0], sp[:, 1])
+    gs = device(2, sp)
+    assert np.array_equal(np.isnan(gs), np.isnan(ws))
+    ok = ~np.isnan(ws)
+    assert np.all((gs[ok] == ws[ok]) | (ulp_error(gs[ok], ws[ok]) <= 2.0))
+    assert gs[0] == 1.0 and gs[1] == 1.0 and gs[2] == 1.0      # 1^y, x^0 and NaN^0 are exactly 1
