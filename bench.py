@@ -558,7 +558,7 @@ def run_ours(args):
 
 
 def run_secondary(args, d_buf, flush, barrier, max_over_ranks, rank, world, local):
-    """BASELINE configs[1] (two-layer 1M), [3] (MAGICC boxes, 100k, fp64 and fp32) and [4] (log-posterior of 1M members and
+    """BASELINE configs[1] (two-layer 1M), [3] (MAGICC boxes, 100k, fp64 and fp32; and the eleven-box emissions-driven chain) and [4] (log-posterior of 1M members and
     the sampler loop with its all-gather).  Configs 2 and 4 do not communicate: at N > 1 every rank runs the same shape
     (weak) and the line reports N x the slowest rank.  Each entry carries kernel time and parity against the CPU oracle."""
     import torch
@@ -568,7 +568,7 @@ def run_secondary(args, d_buf, flush, barrier, max_over_ranks, rank, world, loca
     dev = torch.device("cuda", local)
     res = {}
 
-    def one(name, builder, binds, params, scen, outputs, dtype, n_sub, tol):
+    def one(name, builder, binds, params, scen, outputs, dtype, n_sub, tol, years=YEARS):
         ens = builder.build_ensemble(dtype=dtype, device=local).bind_parameters(binds)
         ens.select_outputs(outputs)
         sc_host = ens.pack_scenarios(scen)
@@ -580,8 +580,8 @@ def run_secondary(args, d_buf, flush, barrier, max_over_ranks, rank, world, loca
         kms = ens.kernel_ms(reset=True)
         par = oracle_check(builder, binds, ens, d_o, params, sc_host, outputs, Mc, Sc, n_sub, tol)
         par.pop("per_series")
-        res[name] = {"value": world * Mc * Sc * YEARS / (ms * 1e-3), "unit": "member-years/s", "ms_per_step": ms, "kernel_ms": kms,
-                     "members_per_gpu": Mc, "scenarios": Sc, "dtype": dtype, "jit": ens.program_is_jit(), "parity": par}
+        res[name] = {"value": world * Mc * Sc * years / (ms * 1e-3), "unit": "member-years/s", "ms_per_step": ms, "kernel_ms": kms,
+                     "members_per_gpu": Mc, "scenarios": Sc, "years": years, "dtype": dtype, "jit": ens.program_is_jit(), "parity": par}
         ens.close()
 
     b, binds, params, scen = syn.config2(M=1 << 20)
@@ -589,6 +589,9 @@ def run_secondary(args, d_buf, flush, barrier, max_over_ranks, rank, world, loca
     b4, binds4, params4, scen4 = syn.config4(M=100_000)
     one("config4_magicc_boxes_100k_f64", b4, binds4, params4, scen4, syn.CONFIG4_OUTPUTS, "f64", 256, 1e-9)
     one("config4_magicc_boxes_100k_f32", b4, binds4, params4, scen4, syn.CONFIG4_OUTPUTS, "f32", 256, 1e-4)
+    # configs[3] at its widest: all eleven rscm-magicc boxes in one emissions-driven graph (124 variables, run-time compiled)
+    bf, bindsf, paramsf, scenf = syn.full_chain(M=100_000)
+    one("config4_full_chain_11_boxes_100k_f64", bf, bindsf, paramsf, scenf, syn.FULL_CHAIN_OUTPUTS, "f64", 64, 1e-9, years=250)
 
     # ---- config 5: log-posterior of 1M two-layer members, then the sampler loop ------------------------------------
     from tests.helpers import oracle_bindings, oracle_from_builder

@@ -446,7 +446,7 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         }
         const double *hist = cx.scratch + static_cast<long long>(nr.scr) * SCR_LD;
         R sum = R(0);
-#pragma unroll 4
+#pragma unroll 8
         for (int i = nhist - 1 - q; i >= first; i -= UDEB_LANES) sum += R(hist[i * SCR_LD]);
         if (q == 0 && partial > R(0) && first > 0) sum += R(hist[(first - 1) * SCR_LD]) * partial;
         X[(UX_HIST + q) * 32] = static_cast<double>(sum);

@@ -322,6 +322,12 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
     if (LOGP && cells_on) obs_accumulate<R, NC>(a, s_obs, 0, cur, ll, bad);
 
     const int T = a.T;
+#ifdef RSCM_NODE_CLOCKS // profiling aid (tools/node_clocks.py): where thread 0 of CTA 0 spends a model year outside the nodes
+    long long loop_clk[3] = {0, 0, 0}, loop_t = clock64();
+#define LOOP_CLK(i) do { const long long now_ = clock64(); loop_clk[i] += now_ - loop_t; loop_t = now_; } while (0)
+#else
+#define LOOP_CLK(i) do { } while (0)
+#endif
     for (int N = 0; N < T - 1; ++N) {
         // Programs whose step is far larger than the instruction cache (the 124-variable MAGICC chain: 128 KB of SASS per
         // model year) keep the warps of a CTA in step, so that they fetch the same instructions together instead of
@@ -335,7 +341,9 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
             }
         }
         cx.N = N;
+        LOOP_CLK(0);
         if (LANES > 1 || !LOGP || active) Prog::template step<R>(P, D, cur, nxt, S, cx, fail);
+        LOOP_CLK(1);
 
         if (WRITE) {
             if (N + 1 == tnext && tnext < a.t_stop) { // block-uniform
@@ -357,7 +365,13 @@ __global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::
 #pragma unroll
             for (int c = 0; c < NC; ++c) cur[c] = nxt[c];
         }
+        LOOP_CLK(2);
     }
+#ifdef RSCM_NODE_CLOCKS
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("loop_clocks exogenous+nan %lld step %lld outputs+likelihood+cells %lld (cycles per year)\n", loop_clk[0] / (T - 1), loop_clk[1] / (T - 1),
+               loop_clk[2] / (T - 1));
+#endif
 
     if (a.status && writer) {
         bool nonfinite = false;

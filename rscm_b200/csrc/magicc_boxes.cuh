@@ -375,25 +375,41 @@ __device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R 
     R total = R(0), fgas = R(0), montreal = R(0), eesc = R(0);
     // on a uniform time axis the decay factors are constants of the graph (host-computed, graph.cpp)
     const bool uniform_dt = static_cast<double>(dt) == tab[HALO_CT * HALO_NS];
-    // One ROLLED loop over the 41 species: unrolled it is 3.5 k instructions of a program that is bound by instruction
-    // fetch.  The dynamic indices put in / out / S of this component into local memory, which in these programs is served
-    // by L2 (shared memory takes most of the SM's L1): four species per trip keep four sets of loads in flight.
-#pragma unroll 4
-    for (int s = 0; s < HALO_NS; ++s) {
-        const double *t = tab + HALO_CT * s;
-        const R lifetime = R(t[0]), conv = R(t[1]), rad_eff = R(t[2]), conc_pi = R(t[3]), loading = R(t[4]), release = R(t[5]);
-        R conc = in[2 * s + 1];
-        if (conc != conc) conc = S[s]; // latest_value: fall back to the last non-NaN value (NaN if there never was one)
-        S[s] = conc;
-        const R decay = uniform_dt ? R(tab[HALO_CT * HALO_NS + 1 + s]) : r_exp_call<R>(-dt / lifetime); // block-uniform choice
-        const R emissions_ppt = in[2 * s] * conv;
-        const R new_conc = conc * decay + emissions_ppt * lifetime * (R(1) - decay);
-        out[s] = new_conc;
-        const R forcing = (new_conc - conc_pi) * rad_eff / R(1000);
-        total += forcing;
-        if (s < HALO_NF) fgas += forcing;
-        else montreal += forcing;
-        if (release > R(0)) eesc += new_conc * loading * release;
+    // ROLLED over the 41 species (unrolled it is 3.5 k instructions of a program that is bound by instruction fetch), in
+    // blocks of eight: the dynamic indices put in / out / S of this component into local memory, which in these programs
+    // is served by L2 (shared memory takes most of the SM's L1), so the 24 loads of a block are issued together, before any
+    // of the block's arithmetic and branches.  The sums keep the species order.
+    constexpr int HB = 8;
+#pragma unroll 1
+    for (int s0 = 0; s0 < HALO_NS; s0 += HB) {
+        R em[HB], cc[HB], sv[HB];
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            const int s = s0 + u < HALO_NS ? s0 + u : HALO_NS - 1;
+            em[u] = in[2 * s];
+            cc[u] = in[2 * s + 1];
+            sv[u] = S[s];
+        }
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            const int s = s0 + u;
+            if (s < HALO_NS) {
+                const double *t = tab + HALO_CT * s;
+                const R lifetime = R(t[0]), conv = R(t[1]), rad_eff = R(t[2]), conc_pi = R(t[3]), loading = R(t[4]), release = R(t[5]);
+                R conc = cc[u];
+                if (conc != conc) conc = sv[u]; // latest_value: fall back to the last non-NaN value (NaN if there never was one)
+                S[s] = conc;
+                const R decay = uniform_dt ? R(tab[HALO_CT * HALO_NS + 1 + s]) : r_exp_call<R>(-dt / lifetime); // block-uniform choice
+                const R emissions_ppt = em[u] * conv;
+                const R new_conc = conc * decay + emissions_ppt * lifetime * (R(1) - decay);
+                out[s] = new_conc;
+                const R forcing = (new_conc - conc_pi) * rad_eff / R(1000);
+                total += forcing;
+                if (s < HALO_NF) fgas += forcing;
+                else montreal += forcing;
+                if (release > R(0)) eesc += new_conc * loading * release;
+            }
+        }
     }
     out[HALO_NS] = total;
     out[HALO_NS + 1] = fgas;

@@ -7,9 +7,8 @@ import pytest
 
 from oracle import oracle as orc
 from rscm_b200 import synthetic as syn
-from rscm_b200.core import GridType, ModelBuilder, VariableSchema
-from rscm_b200.magicc import (AerosolDirectBuilder, AerosolIndirectBuilder, CH4ChemistryBuilder, ClimateUDEBBuilder, CO2BudgetBuilder,
-                              GhgForcingBuilder, N2OChemistryBuilder, OceanCarbonBuilder, OzoneForcingBuilder, TerrestrialCarbonBuilder)
+from rscm_b200.core import ModelBuilder
+from rscm_b200.magicc import OceanCarbonBuilder
 
 from .helpers import oracle_bindings, oracle_from_builder, rel_err
 
@@ -98,66 +97,8 @@ def test_ocean_carbon_gpu_parity(model, tmp_path, monkeypatch):
         assert rel_err(got[n], ref[n]) <= 1e-9, n
 
 
-def full_magicc_builder(start=1850, end=1950, halocarbons=False):
-    """Emissions-driven MAGICC: CH4/N2O chemistry, terrestrial + ocean carbon, CO2 budget, GHG / ozone / aerosol forcing,
-    Sum aggregate (with an initial value), ClimateUDEB on the four-box grid.  ``halocarbons=True`` wires HalocarbonChemistry in:
-    its EESC replaces the exogenous one and Forcing|Halocarbons joins the ERF aggregate."""
-    from rscm_b200.magicc import HalocarbonChemistryBuilder
-    species = HalocarbonChemistryBuilder.species_names() if halocarbons else []
-    erf_parts = list(syn.CONFIG4_ERF_PARTS) + (["Forcing|Halocarbons"] if halocarbons else [])
-    schema = VariableSchema()
-    for s in species:
-        schema.add_variable(f"Emissions|{s}", "kt/yr")
-        schema.add_variable(f"Atmospheric Concentration|{s}", "ppt")
-    for n in (("Forcing|Halocarbons", "Forcing|F-gases", "Forcing|Montreal Gases") if halocarbons else ()):
-        schema.add_variable(n, "W/m^2")
-    for n in ("CH4", "N2O", "NOx", "CO", "NMVOC", "SOx", "BC", "OC", "CO2|Fossil", "CO2|Land Use"):
-        schema.add_variable(f"Emissions|{n}", "")
-    schema.add_variable("EESC", "ppt")
-    for n in ("CO2", "CH4", "N2O"):
-        schema.add_variable(f"Atmospheric Concentration|{n}", "")
-    for n in syn.CONFIG4_ERF_PARTS:
-        schema.add_variable(n, "W/m^2")
-    schema.add_variable("Surface Temperature", "K", GridType.FourBox)
-    for n in ("Heat Uptake", "Ocean Heat Content", "Sea Surface Temperature", "Carbon Flux|Terrestrial", "Carbon Flux|Ocean", "Carbon Pool|Plant",
-              "Carbon Pool|Detritus", "Carbon Pool|Soil", "Carbon Pool|Humus", "Ocean Surface pCO2", "Cumulative Ocean Uptake",
-              "Emissions|CO2|Net", "Airborne Fraction|CO2", "Lifetime|CH4", "Lifetime|N2O"):
-        schema.add_variable(n, "")
-    schema.add_aggregate("Effective Radiative Forcing", "W/m^2", "Sum", erf_parts)
-    b = ModelBuilder().with_time_axis(syn.time_axis(start, end)).with_schema(schema)
-    if halocarbons:
-        b = (b.with_rust_component(HalocarbonChemistryBuilder.from_parameters({}).build())
-             .with_initial_values({f"Atmospheric Concentration|{s}": (500.0 if s == "CH3Cl" else 5.0 if s == "CH3Br" else 0.0) for s in species}))
-    return (
-        b
-        .with_rust_component(CH4ChemistryBuilder.from_parameters({}).build())
-        .with_rust_component(N2OChemistryBuilder.from_parameters({}).build())
-        .with_rust_component(TerrestrialCarbonBuilder.from_parameters({}).build())
-        .with_rust_component(OceanCarbonBuilder.from_parameters({}).build())
-        .with_rust_component(CO2BudgetBuilder.from_parameters({}).build())
-        .with_rust_component(GhgForcingBuilder.from_parameters({"method": "Ipcctar"}).build())
-        .with_rust_component(OzoneForcingBuilder.from_parameters({}).build())
-        .with_rust_component(AerosolDirectBuilder.from_parameters({}).build())
-        .with_rust_component(AerosolIndirectBuilder.from_parameters({}).build())
-        .with_rust_component(ClimateUDEBBuilder.from_parameters({}).build())
-        .with_initial_values({"Atmospheric Concentration|CH4": 722.0, "Atmospheric Concentration|N2O": 270.0,
-                              "Atmospheric Concentration|CO2": 278.0, "Carbon Pool|Plant": 884.86, "Carbon Pool|Detritus": 92.77,
-                              "Carbon Pool|Soil": 1681.53, "Carbon Pool|Humus": 836.0, "Ocean Surface pCO2": 278.0,
-                              "Cumulative Ocean Uptake": 0.0, "Surface Temperature": 0.0, "Effective Radiative Forcing": 0.0,
-                              "Sea Surface Temperature": 0.0, "Carbon Flux|Terrestrial": 0.0, "Carbon Flux|Ocean": 0.0})
-    )
-
-
-def full_magicc_scenario(start=1850, end=1950, f=1.0):
-    years = syn.time_axis(start, end).values()
-    ramp = (years - start) / 100.0
-    return {"Emissions|CH4": 50.0 + 250.0 * ramp * f, "Emissions|N2O": 1.0 + 6.0 * ramp, "Emissions|NOx": 5.0 + 30.0 * ramp,
-            "Emissions|CO": 100.0 + 500.0 * ramp, "Emissions|NMVOC": 20.0 + 100.0 * ramp, "Emissions|SOx": 1.0 + 50.0 * ramp,
-            "Emissions|BC": 2.5 + 4.0 * ramp, "Emissions|OC": 10.0 + 15.0 * ramp, "Emissions|CO2|Fossil": 8.0 * ramp ** 2 * f,
-            "Emissions|CO2|Land Use": 0.5 + 0.8 * ramp, "EESC": 1000.0 + 900.0 * ramp}
-
-
-FULL_BINDS = {"ecs": "ClimateUDEB.ecs", "beta": "TerrestrialCarbon.beta", "tau": "OceanCarbon.gas_exchange_tau", "tau_oh": "CH4Chemistry.tau_oh"}
+# the emissions-driven chain itself lives in rscm_b200/synthetic.py (bench.py times it as BASELINE config 4's widest graph)
+full_magicc_builder, full_magicc_scenario, FULL_BINDS = syn.full_chain_builder, syn.full_chain_scenario, syn.FULL_CHAIN_BINDINGS
 
 
 def test_full_magicc_graph_on_the_oracle():

@@ -196,16 +196,8 @@ def sampler_loop_distributed(W=1 << 20, iters=30):
 def full_magicc(M=37_888):
     """Not a BASELINE config: the emissions-driven MAGICC chain of the reference's regression suite (11 components incl.
     HalocarbonChemistry, 124 variables, run-time compiled), 1850-2100, as a throughput data point."""
-    from tests.test_halocarbon import ramp_scenario
-    from tests.test_ocean_carbon import FULL_BINDS, full_magicc_builder, full_magicc_scenario
-    b = full_magicc_builder(end=2100, halocarbons=True)
-    ens = b.build_ensemble().bind_parameters(FULL_BINDS)
-    s = full_magicc_scenario(end=2100)
-    s.pop("EESC")
-    s.update(ramp_scenario(251))
-    outs = ["Surface Temperature", "Atmospheric Concentration|CO2", "Atmospheric Concentration|CH4", "Effective Radiative Forcing", "EESC"]
-    params = syn.uniform_params({"ecs": (2.0, 4.5), "beta": (0.4, 0.9), "tau": (6.5, 9.5), "tau_oh": (8.5, 10.5)}, M, 43)
-    run_config("full MAGICC chain (11 components, 124 variables) %d members" % M, b, FULL_BINDS, params, [s], outs, "f64", 997, years=250)
+    b, binds, params, scen = syn.full_chain(M=M)
+    run_config("full MAGICC chain (11 components, 124 variables) %d members" % M, b, binds, params, scen, syn.FULL_CHAIN_OUTPUTS, "f64", 997, years=250)
 
 
 def summaries(M=262_144):

@@ -17,15 +17,10 @@ from rscm_b200 import synthetic as syn
 which = sys.argv[1] if len(sys.argv) > 1 else "magicc"
 M = 148 * 3 * 32
 if which == "magicc":
-    from tests.test_ocean_carbon import FULL_BINDS, full_magicc_builder, full_magicc_scenario
-    b = full_magicc_builder(end=2100, halocarbons=True)
-    ens = b.build_ensemble().bind_parameters(FULL_BINDS)
-    from tests.test_halocarbon import ramp_scenario
-    scen = full_magicc_scenario(end=2100)
-    scen.pop("EESC")
-    scen.update(ramp_scenario(251))
-    params = syn.uniform_params({"ecs": (2.0, 4.5), "beta": (0.4, 0.9), "tau": (6.5, 9.5), "tau_oh": (8.5, 10.5)}, M, 43)
-    ens.select_outputs(["Surface Temperature", "Atmospheric Concentration|CO2", "Atmospheric Concentration|CH4", "Effective Radiative Forcing", "EESC"])
+    b, binds, params, scens = syn.full_chain(M=M)
+    scen = scens[0]
+    ens = b.build_ensemble().bind_parameters(binds)
+    ens.select_outputs(syn.FULL_CHAIN_OUTPUTS)
 else:
     axis = syn.time_axis(1850, 2100)
     b = syn.config4_builder(axis)
