@@ -532,8 +532,17 @@ static void emit_program(Graph &g)
     // 8 CTAs of 128 threads per SM = 64 registers per thread; register-hungry programs get 4 (128 registers)
     // programs with per-thread shared-memory scratch are limited by shared memory, not registers (2 = no register cap;
     // two CTAs fit one SM in fp32)
-    // programs whose members span several lanes keep rows of state in registers: 3 CTAs = 168 registers per thread
+    // Programs whose members span several lanes (ClimateUDEB) are bound by latency — dependent chains, two rendezvous per
+    // sub-step — with a few warps per scheduler, so the CTAs per SM matter more than a spill-free register allocation:
+    // 4 CTAs (128 registers, about 200 B of spills per thread) where the shared memory of four fits one SM, measured
+    // 3.06e8 against 2.66e8 member-years/s with 3 CTAs (168 registers) on config 4.  The exogenous rows then stay in
+    // global memory (L2; 28 KB per CTA at config 4 — staging them is worth 3 % only when it costs no CTA).
     int lanes_blocks = 3;
+    const int tpad = (g.T + 3) / 4 * 4;
+    const long lanes_smem = 16 + 1024 /*static + reserved per CTA*/ + (g.needs_time ? (tpad + 4) * 8L : 0) + static_cast<long>(g.ctab.size()) * 8 +
+                            static_cast<long>(g.n_rk) * tpad * 4 + g.n_smem * 1024L + g.n_xch * 256L + 2L * 2 * tpad * 8 /*two observed variables*/;
+    const long exo_smem = static_cast<long>(g.n_exo_rows) * tpad * 8;
+    if (g.lanes > 1 && lanes_smem <= 232448 / 4) lanes_blocks = 4;
     if (const char *e = std::getenv("RSCM_B200_LANES_MIN_BLOCKS")) lanes_blocks = std::max(1, std::min(8, std::atoi(e))); // tuning knob
     o << "    static constexpr int MIN_BLOCKS = " << (g.lanes > 1 ? lanes_blocks : (g.n_smem > 0 ? 2 : (weight <= 32 ? 8 : 4))) << ";\n";
     o << "    static constexpr int NS = " << g.n_state << ";\n";
@@ -547,6 +556,8 @@ static void emit_program(Graph &g)
     o << "    static constexpr bool NEEDS_TIME = " << (g.needs_time ? "true" : "false") << ";\n";
     // exogenous rows are staged into shared memory unless per-thread scratch or a long row list needs the space
     g.stage_exo = (g.n_smem == 0 || g.lanes > 1) && g.n_exo_rows <= 24;
+    if (g.lanes > 1 && lanes_smem + exo_smem > 232448 / lanes_blocks) g.stage_exo = false; // not at the price of a CTA per SM
+    if (g.lanes > 1 && std::getenv("RSCM_B200_LANES_STAGE_EXO")) g.stage_exo = std::atoi(std::getenv("RSCM_B200_LANES_STAGE_EXO")) != 0; // tuning knob
     o << "    static constexpr bool STAGE_EXO = " << (g.stage_exo ? "true" : "false") << ";\n";
     o << "    __host__ __device__ static constexpr int exo_row(int c) { return ";
     for (int c = 0; c < g.n_cells; ++c) {

@@ -174,7 +174,9 @@ template <class Prog> struct ProgSpec<Prog, decltype(void(Prog::SPECIALIZED))> {
 };
 
 template <class R, class Prog, bool WRITE, bool LOGP>
-__global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::MIN_BLOCKS - 1 : Prog::MIN_BLOCKS) ensemble_kernel(const __grid_constant__ KArgs a)
+__global__ void __launch_bounds__(BLOCK, (LOGP && Prog::MIN_BLOCKS > 4) ? Prog::MIN_BLOCKS - 1
+                                         : (Prog::LANES > 1 && sizeof(R) == 4 && Prog::MIN_BLOCKS == 4) ? 5 // fp32 rows are half the registers
+                                                                                                        : Prog::MIN_BLOCKS) ensemble_kernel(const __grid_constant__ KArgs a)
 {
     constexpr int NC = Prog::NC;
     constexpr int NP = Prog::NP;

@@ -31,13 +31,17 @@ def one():
         ref = m.run_batch(oracle_bindings(b, binds), params[idx], ens.exogenous_names, sc_host, syn.CONFIG4_OUTPUTS)
         got, want = ens.split_outputs(sub), m.split(ref, syn.CONFIG4_OUTPUTS)
         err = max(rel_err(got[n], want[n]) for n in syn.CONFIG4_OUTPUTS)
-        print(json.dumps({"min_blocks": os.environ.get("RSCM_B200_LANES_MIN_BLOCKS", "default"), "dtype": dt, "members": M, "kernel_ms": ms,
+        print(json.dumps({"min_blocks": os.environ.get("RSCM_B200_LANES_MIN_BLOCKS", "default"), "stage_exo": os.environ.get("RSCM_B200_LANES_STAGE_EXO", "default"),
+                          "smem": ens.shared_bytes(), "dtype": dt, "members": M, "kernel_ms": ms,
                           "member_years_per_s": M * 350 / (ms * 1e-3), "max_rel_err": err}), flush=True)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         one()
     else:
-        for mb in (sys.argv[1:] or ["2", "3", "4"]):
-            env = dict(os.environ, RSCM_B200_LANES_MIN_BLOCKS=mb, RSCM_B200_CACHE=f"/tmp/rscm_cache_mb{mb}")
+        for mb in (sys.argv[1:] or ["2", "3", "4"]):       # "3" or "4:0" = CTAs per SM [: exogenous rows staged in shared memory 0/1]
+            mb, _, st = mb.partition(":")
+            env = dict(os.environ, RSCM_B200_LANES_MIN_BLOCKS=mb, RSCM_B200_CACHE=f"/tmp/rscm_cache_mb{mb}_{st}")
+            if st:
+                env["RSCM_B200_LANES_STAGE_EXO"] = st
             subprocess.run([sys.executable, __file__, "one"], env=env, check=False)
