@@ -412,11 +412,9 @@ static const std::vector<KindInfo> &kinds()
           0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
           1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0},
          48, /*n_state*/ 2, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10,
-         /*scratch_fixed*/ 0, /*no_slots*/ false, /*lanes*/ 1, /*aux_template*/ false,
-         /*n_smem_lanes: as one CTA-wide region, two staged history tiles (16 words x 128 threads = 2 x 32 months x 32
-           members); then, per thread, the block-prefix sums of the convolution (one word per month of the year:
-           smem_lanes_per_aux) — magicc_boxes.cuh*/ 16, /*lane_aware*/ true, /*n_xch: the tiles' two mbarriers*/ 1,
-         /*smem_lanes_per_aux*/ true},
+         /*scratch_fixed: 4 x 16 rows of block-prefix sums before the history (OCEAN_HIST0)*/ 64, /*no_slots*/ false, /*lanes*/ 1, /*aux_template*/ false,
+         /*n_smem_lanes: as one CTA-wide region, two staged history tiles (8 words x 128 threads = 2 x 16 months x 32
+           members, OCEAN_KT in magicc_boxes.cuh)*/ 8, /*lane_aware*/ true, /*n_xch: the tiles' two mbarriers*/ 1},
     };
     static const bool extended = (k.push_back(halocarbon_kind()), true);
     (void)extended;
@@ -540,7 +538,7 @@ static void emit_program(Graph &g)
     int lanes_blocks = 3;
     const int tpad = (g.T + 3) / 4 * 4;
     const long lanes_smem = 16 + 1024 /*static + reserved per CTA*/ + (g.needs_time ? (tpad + 4) * 8L : 0) + static_cast<long>(g.ctab.size()) * 8 +
-                            static_cast<long>(g.n_rk) * tpad * 4 + g.n_smem * 1024L + g.n_xch * 256L + 2L * 2 * tpad * 8 /*two observed variables*/;
+                            static_cast<long>(g.n_rk) * tpad * 4 + g.n_smem * 1024L + g.n_xch * 256L + 2L * tpad * 8 /*one observed variable*/;
     const long exo_smem = static_cast<long>(g.n_exo_rows) * tpad * 8;
     if (g.lanes > 1 && lanes_smem <= 232448 / 4) lanes_blocks = 4;
     if (const char *e = std::getenv("RSCM_B200_LANES_MIN_BLOCKS")) lanes_blocks = std::max(1, std::min(8, std::atoi(e))); // tuning knob
@@ -1038,8 +1036,7 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         n.scratch_base = g.n_scratch_rows;
         n.ctab_base = static_cast<int>(g.ctab.size());
         g.n_state += k->n_state;
-        // (lane-group programs: n_smem_lanes fixed words, plus one per unit of the aux parameter for the kinds that say so)
-        g.n_smem += k->n_smem + (g.lanes > 1 ? k->n_smem_lanes + (k->smem_lanes_per_aux ? n.aux : 0) : 0);
+        g.n_smem += k->n_smem + (g.lanes > 1 ? k->n_smem_lanes : 0);
         if (g.lanes > 1 && (k->lanes > 1 || k->lane_aware)) {
             // a lane node: its input values travel from role 0 to the other roles through the first exchange slots
             n.lane_node = true;

@@ -59,7 +59,6 @@ struct KindInfo {
     // may use n_xch further exchange slots (doubles per member) of its own.
     bool lane_aware = false;
     int n_xch = 0;
-    bool smem_lanes_per_aux = false; // lane-group programs: aux (the literal of aux_param) further words per thread after n_smem_lanes
 };
 
 const KindInfo *kind_info(int kind);

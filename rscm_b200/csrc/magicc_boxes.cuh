@@ -196,9 +196,12 @@ __device__ __forceinline__ bool n2o_chemistry_solve(const R *P, const R *, const
 //     rows, and none of it through L1, which holds the spilled cells of these large programs.  The accumulation order
 //     per month is unchanged (history before the block, then the block, oldest first).
 // P: see include/rscm_b200.h (60 values); S[0] = months of history so far, S[1] = tiles staged so far (mbarrier phase).
-// Shared memory of the node in lane-group programs: as one CTA-wide region, words [0,16) x 128 threads are the two tiles
-// [2][OCEAN_KT][32]; then `steps` words per thread for the prefix sums.  The tiles' two mbarriers are the node's exchange slot.
-constexpr int OCEAN_KT = 32;
+// Shared memory of the node in lane-group programs: as one CTA-wide region, OCEAN_KT / 2 words x 128 threads are the two
+// tiles [2][OCEAN_KT][32] (graph.cpp: n_smem_lanes); the tiles' two mbarriers are the node's exchange slot.  The prefix sums
+// wait for their year in the first 4 x 16 rows of the node's global scratch (row 16 q + m: month m of the block's year q;
+// 12 values per member and year through L2), the flux history follows from row OCEAN_HIST0 on.
+constexpr int OCEAN_KT = 16;
+constexpr int OCEAN_HIST0 = 64;
 template <class R> __device__ __forceinline__ void ocean_carbon_prepare(const R *P, R *D)
 {
     D[0] = P[3] / (P[4] * R(12));            // gas_exchange_rate
@@ -227,7 +230,8 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     const R k_gas = D[0], dic_conv = D[1];
     const int n_old = static_cast<int>(S[0]);
     const double *irf = cx.gtab + nr.gt;
-    double *hist = cx.scratch + static_cast<long long>(nr.scr) * SCR_LD;
+    double *pre = cx.scratch + static_cast<long long>(nr.scr) * SCR_LD;      // prefix sums of the block of four years (lane groups)
+    double *hist = pre + OCEAN_HIST0 * SCR_LD;
     R acc[MAXS];
     // sum over history entries [i0, i1) (entry i at src[i * SCR_LD]: the global scratch, or a staged tile, which has the
     // same row length) against the lags of months `first_month + m` (m < steps), oldest entry first.  Chunks of 16 months:
@@ -263,7 +267,6 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     const int max_hist = static_cast<int>(P[11]);
     auto oldest = [&](int first_month) { const int lo = first_month + 1 - max_hist; return lo > 0 ? (lo < n_old ? lo : n_old) : 0; };
     if (cx.lanes == 4) {
-        R *A = cx.sm + (nr.sm + 16) * BLOCK * (8 / static_cast<int>(sizeof(R))); // this thread's prefix sums, month m at A[m * BLOCK]
         const int yb = (n_old / steps) & 3;                               // year within the block of four (CTA-uniform)
         if (yb == 0) {
             const int first_month = n_old + steps * cx.role;              // role q prepares year q of the block
@@ -294,19 +297,19 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
                 if (threadIdx.x == 0 && t + 2 < nt) stage(t + 2);
             }
             S[1] = R(tc + nt);
+            if (cx.live) {
 #pragma unroll
-            for (int m = 0; m < MAXS; ++m)
-                if (m < steps) A[m * BLOCK] = acc[m];
+                for (int m = 0; m < MAXS; ++m)
+                    if (m < steps) pre[(16 * cx.role + m) * SCR_LD] = static_cast<double>(acc[m]);
+            }
         }
-        __syncthreads();
+        __syncthreads(); // (also makes the prefix sums, written by the member's other roles, visible to role 0)
         if (cx.role != 0) { // the other roles only help with the long history; role 0 steps the months
             S[0] = R(n_old + steps);
             return true;
         }
-        // the column of the role that prepared this year: thread ((yb - rot) & 3) * 32 + lane, this one (role 0) is ((-rot) & 3) * 32 + lane
-        const R *Ay = A + ((((yb - cx.rot) & 3) - ((-cx.rot) & 3)) * 32);
 #pragma unroll
-        for (int m = 0; m < MAXS; ++m) acc[m] = (m < steps) ? Ay[m * BLOCK] : R(0);
+        for (int m = 0; m < MAXS; ++m) acc[m] = (m < steps) ? R(pre[(16 * yb + m) * SCR_LD]) : R(0); // the sums role yb prepared
         convolve(hist, n_old - yb * steps, n_old, n_old); // the block's own months so far (just written: L1 / L2 resident)
     } else {
 #pragma unroll
