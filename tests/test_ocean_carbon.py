@@ -169,3 +169,56 @@ def test_full_magicc_truncated_history_in_lane_quads(tmp_path, monkeypatch):
     ref = m.split(m.run_batch(oracle_bindings(b, FULL_BINDS), p, ens.exogenous_names, sc, names), names)
     for n in names:
         assert rel_err(got[n], ref[n]) <= 1e-9, n
+
+
+@pytest.mark.gpu
+def test_eleven_box_chain_ragged_members_and_log_posterior(tmp_path, monkeypatch):
+    """The widest graph (HalocarbonChemistry included: 124 variables, cells swapped by pointer, OceanCarbon's history staged by
+    bulk copies) with a member count that leaves padding lanes in the second CTA, two scenarios, 150 years (37 blocks of four
+    years, up to 113 staged tiles per block), and the log-posterior variant of the same program."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    from rscm_b200 import _ffi
+    b, binds, p, scen = syn.full_chain(M=45, end=2000)
+    scen2 = dict(scen[0])
+    scen2["Emissions|CO2|Fossil"] = scen2["Emissions|CO2|Fossil"] * 1.4
+    scen2["Emissions|CFC-12"] = scen2["Emissions|CFC-12"] * 0.5
+    ens = b.build_ensemble().bind_parameters(binds)
+    assert ens.program_is_jit() and "SWAP_CELLS = true" in ens.program_signature() and "LANES = 4" in ens.program_signature()
+    sc = ens.pack_scenarios([scen[0], scen2])
+    names = syn.FULL_CHAIN_OUTPUTS + ["Ocean Surface pCO2", "Atmospheric Concentration|CFC-12", "Forcing|Halocarbons", "Ocean Heat Content"]
+    ens.select_outputs(names)
+    got = ens.split_outputs(ens.run(p, sc))
+    m = oracle_from_builder(b)
+    ob = oracle_bindings(b, binds)
+    ref = m.split(m.run_batch(ob, p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
+    obs = [("Atmospheric Concentration|CO2", float(y), 300.0 + 0.5 * (y - 1900), 8.0) for y in range(1900, 2001, 20)] + \
+          [("Surface Temperature", float(y), 0.4, 0.3) for y in range(1950, 2001, 25)]
+    priors = [(_ffi.PRIOR_UNIFORM, 1.5, 5.0), (_ffi.PRIOR_UNIFORM, 0.3, 1.0), (_ffi.PRIOR_NORMAL, 8.0, 2.0), (_ffi.PRIOR_UNIFORM, 8.0, 11.0)]
+    ens.set_target(obs).set_priors(priors)
+    lp, summ = ens.log_posterior(p, sc, with_summary=True)
+    want = m.log_posterior_batch(ob, p, ens.exogenous_names, sc, priors, obs)
+    fin = np.isfinite(want)
+    assert fin.any() and np.array_equal(np.isfinite(lp), fin)
+    assert np.max(np.abs(lp[fin] - want[fin]) / np.abs(want[fin])) <= 1e-9
+    assert summ["n_runs"] == 90 and summ["n_finite"] == int(fin.sum())
+
+
+def test_lane_group_programs_are_sized_for_four_ctas_per_sm():
+    """graph.cpp picks the CTAs per SM a lane-group program is compiled for from its shared-memory footprint: four where four
+    CTAs fit the SM's 227 KB (then the exogenous rows stay in global memory), else three."""
+    import re
+    b4, binds4, _, _ = syn.config4(M=4)
+    e4 = b4.build_ensemble(device=-2).bind_parameters(binds4)
+    sig4 = e4.program_signature()
+    assert "LANES = 4" in sig4 and "MIN_BLOCKS = 4" in sig4 and "STAGE_EXO = false" in sig4
+    assert 4 * (e4.shared_bytes() + 1024) <= 232448
+    bf, bindsf, _, _ = syn.full_chain(M=4)
+    ef = bf.build_ensemble(device=-2).bind_parameters(bindsf)
+    sigf = ef.program_signature()
+    assert "MIN_BLOCKS = 4" in sigf and "SWAP_CELLS = true" in sigf and 4 * (ef.shared_bytes() + 1024) <= 232448
+    assert ef.shared_bytes(log_posterior=True) >= ef.shared_bytes()
+    # thread-per-member programs keep their exogenous rows in shared memory
+    sig2 = syn.config2(M=4)[0].build_ensemble(device=-2).program_signature()
+    assert "LANES = 1" in sig2 and "STAGE_EXO = true" in sig2 and int(re.search(r"MIN_BLOCKS = (\d+)", sig2).group(1)) == 8

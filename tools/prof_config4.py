@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""Short config-4 run (MAGICC boxes + ClimateUDEB) for ncu: one wave of the lane-quad kernel (148 SMs x 3 CTAs x 32 members), 60 years."""
+"""Short config-4 run (MAGICC boxes + ClimateUDEB) for ncu: one wave of the lane-group kernel (148 SMs x 4 CTAs x 32 members), 60 years."""
 import os, sys
 import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rscm_b200 import synthetic as syn
 
-M = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 3 * 32
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 4 * 32
 axis = syn.time_axis(1850, 1910)
 b = syn.config4_builder(axis)
 params = syn.uniform_params(syn.CONFIG4_RANGES, M, 7)
