@@ -194,7 +194,7 @@ def test_eleven_box_chain_ragged_members_and_log_posterior(tmp_path, monkeypatch
     for n in names:
         assert rel_err(got[n], ref[n]) <= 1e-9, n
     obs = [("Atmospheric Concentration|CO2", float(y), 300.0 + 0.5 * (y - 1900), 8.0) for y in range(1900, 2001, 20)] + \
-          [("Surface Temperature", float(y), 0.4, 0.3) for y in range(1950, 2001, 25)]
+          [("Sea Surface Temperature", float(y), -0.2, 0.3) for y in range(1950, 2001, 25)]
     priors = [(_ffi.PRIOR_UNIFORM, 1.5, 5.0), (_ffi.PRIOR_UNIFORM, 0.3, 1.0), (_ffi.PRIOR_NORMAL, 8.0, 2.0), (_ffi.PRIOR_UNIFORM, 8.0, 11.0)]
     ens.set_target(obs).set_priors(priors)
     lp, summ = ens.log_posterior(p, sc, with_summary=True)
