@@ -225,7 +225,7 @@ static KindInfo halocarbon_kind()
     k.rk_step_param = -2;
     k.bindable.assign(k.param_names.size(), 0);
     k.reg_weight = 48;
-    k.n_state = kHaloNS; // last non-NaN concentration per species (Timeseries::latest_value)
+    k.n_state = kHaloNS + 1; // last non-NaN concentration per species (Timeseries::latest_value); [41]: species shared among lanes
     k.needs_time = true;
     // every input through InputState::get_global (mode 3)
     for (int i = 0; i < 2 * kHaloNS; ++i) k.in_access.push_back({i, 3});
@@ -1092,6 +1092,14 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         }
     }
     if (g.ctab.size() % 2) g.ctab.push_back(0.0); // keep every staged section a 16-byte multiple
+    // HalocarbonChemistry: aux = 1 when every species' emissions are exogenous — then the members of a warp (one scenario)
+    // see the same emissions, and the device code may share the 41 species among the lanes (magicc_boxes.cuh)
+    for (Node &n : g.nodes) {
+        if (n.kind != RSCM_B200_HALOCARBON_CHEMISTRY) continue;
+        bool exo = true;
+        for (size_t i = 0; i < n.in_src.size(); i += 2) exo = exo && n.in_src[i] == RSCM_B200_SRC_EXOGENOUS;
+        n.aux = exo ? 1 : 0;
+    }
     emit_program(g);
     return true;
 }

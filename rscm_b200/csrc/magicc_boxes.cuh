@@ -368,6 +368,23 @@ template <class R> __device__ inline void halocarbon_chemistry_init_state(const 
 {
 #pragma unroll
     for (int s = 0; s < HALO_NS; ++s) S[s] = r_nan<R>();
+    S[HALO_NS] = R(0);
+}
+
+// One species, one step (decay_species :115-134, species_forcing :137-145)
+template <class R>
+__device__ __forceinline__ void halocarbon_species(const double *tab, int s, bool uniform_dt, R dt, R emissions, R conc_in, R &good, R &new_conc,
+                                                   R &forcing)
+{
+    const double *t = tab + HALO_CT * s;
+    const R lifetime = R(t[0]), conv = R(t[1]), rad_eff = R(t[2]), conc_pi = R(t[3]);
+    R conc = conc_in;
+    if (conc != conc) conc = good; // latest_value: fall back to the last non-NaN value (NaN if there never was one)
+    good = conc;
+    const R decay = uniform_dt ? R(tab[HALO_CT * HALO_NS + 1 + s]) : r_exp_call<R>(-dt / lifetime); // block-uniform choice
+    const R emissions_ppt = emissions * conv;
+    new_conc = conc * decay + emissions_ppt * lifetime * (R(1) - decay);
+    forcing = (new_conc - conc_pi) * rad_eff / R(1000);
 }
 
 template <class R>
@@ -378,6 +395,64 @@ __device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R 
     R total = R(0), fgas = R(0), montreal = R(0), eesc = R(0);
     // on a uniform time axis the decay factors are constants of the graph (host-computed, graph.cpp)
     const bool uniform_dt = static_cast<double>(dt) == tab[HALO_CT * HALO_NS];
+    // Lane-group programs, all emissions exogenous (nr.aux): the 32 members of the warp belong to one scenario, so unless a
+    // species' initial concentration is bound per member they all compute the same 41 species.  Then lane l computes species
+    // l and l + 32 only (its own last-good values in S[0], S[1]), and every lane collects the results by shuffles, adding the
+    // forcings in species order — the same operations on the same values as the member-by-member form, at a fraction of
+    // its 200 local-memory operations per member-year.  Decided at the first step by comparing the lanes' concentrations.
+    if (cx.lanes > 1 && nr.aux != 0) {
+        const int lane = static_cast<int>(threadIdx.x) & 31;
+        if (cx.N == 0) {
+            bool same = true;
+#pragma unroll 1
+            for (int s = 0; s < HALO_NS; ++s) {
+                const R c = in[2 * s + 1];
+                const R c0 = __shfl_sync(0xffffffffu, c, 0); // (every lane takes part in every shuffle: not under the && below)
+                same = same && c == c0;                      // (a NaN compares unequal: member-by-member form)
+            }
+            S[HALO_NS] = __all_sync(0xffffffffu, same) ? R(1) : R(0);
+        }
+        if (S[HALO_NS] != R(0)) {
+#ifdef RSCM_NODE_CLOCKS
+            __shared__ long long halo_clk[3];
+            const bool clk_on = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+            if (clk_on && cx.N == 0) halo_clk[0] = halo_clk[1] = halo_clk[2] = 0;
+            long long clk_t = clock64();
+#define HALO_CLK(i) do { if (clk_on) { const long long now_ = clock64(); halo_clk[i] += now_ - clk_t; clk_t = now_; } } while (0)
+#else
+#define HALO_CLK(i) do { } while (0)
+#endif
+            const int sa = lane, sb = lane + 32 < HALO_NS ? lane + 32 : HALO_NS - 1; // (lanes 9.. repeat the last species, unused)
+            R nca, fa, ncb, fb;
+            {
+                const R ea = in[2 * sa], ca = in[2 * sa + 1], eb = in[2 * sb], cb = in[2 * sb + 1];
+                halocarbon_species<R>(tab, sa, uniform_dt, dt, ea, ca, S[0], nca, fa);
+                halocarbon_species<R>(tab, sb, uniform_dt, dt, eb, cb, S[1], ncb, fb);
+            }
+            HALO_CLK(0); // this lane's two species
+#pragma unroll 1
+            for (int s = 0; s < HALO_NS; ++s) {
+                const R new_conc = __shfl_sync(0xffffffffu, s < 32 ? nca : ncb, s & 31);
+                const R forcing = __shfl_sync(0xffffffffu, s < 32 ? fa : fb, s & 31);
+                const R loading = R(tab[HALO_CT * s + 4]), release = R(tab[HALO_CT * s + 5]);
+                out[s] = new_conc;
+                total += forcing;
+                if (s < HALO_NF) fgas += forcing;
+                else montreal += forcing;
+                if (release > R(0)) eesc += new_conc * loading * release;
+            }
+            out[HALO_NS] = total;
+            out[HALO_NS + 1] = fgas;
+            out[HALO_NS + 2] = montreal;
+            out[HALO_NS + 3] = eesc;
+            HALO_CLK(1); // collecting the 41 species and the ordered sums
+#ifdef RSCM_NODE_CLOCKS
+            if (clk_on && cx.N == cx.n_steps - 1)
+                printf("halocarbon_clocks own_species %lld collect %lld (cycles per year)\n", halo_clk[0] / cx.n_steps, halo_clk[1] / cx.n_steps);
+#endif
+            return true;
+        }
+    }
     // ROLLED over the 41 species (unrolled it is 3.5 k instructions of a program that is bound by instruction fetch), in
     // blocks of eight: the dynamic indices put in / out / S of this component into local memory, which in these programs
     // is served by L2 (shared memory takes most of the SM's L1), so the 24 loads of a block are issued together, before any
@@ -397,16 +472,11 @@ __device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R 
         for (int u = 0; u < HB; ++u) {
             const int s = s0 + u;
             if (s < HALO_NS) {
-                const double *t = tab + HALO_CT * s;
-                const R lifetime = R(t[0]), conv = R(t[1]), rad_eff = R(t[2]), conc_pi = R(t[3]), loading = R(t[4]), release = R(t[5]);
-                R conc = cc[u];
-                if (conc != conc) conc = sv[u]; // latest_value: fall back to the last non-NaN value (NaN if there never was one)
-                S[s] = conc;
-                const R decay = uniform_dt ? R(tab[HALO_CT * HALO_NS + 1 + s]) : r_exp_call<R>(-dt / lifetime); // block-uniform choice
-                const R emissions_ppt = em[u] * conv;
-                const R new_conc = conc * decay + emissions_ppt * lifetime * (R(1) - decay);
+                R new_conc, forcing;
+                halocarbon_species<R>(tab, s, uniform_dt, dt, em[u], cc[u], sv[u], new_conc, forcing);
+                S[s] = sv[u];
                 out[s] = new_conc;
-                const R forcing = (new_conc - conc_pi) * rad_eff / R(1000);
+                const R loading = R(tab[HALO_CT * s + 4]), release = R(tab[HALO_CT * s + 5]);
                 total += forcing;
                 if (s < HALO_NF) fgas += forcing;
                 else montreal += forcing;

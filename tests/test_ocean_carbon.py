@@ -222,3 +222,34 @@ def test_lane_group_programs_are_sized_for_four_ctas_per_sm():
     # thread-per-member programs keep their exogenous rows in shared memory
     sig2 = syn.config2(M=4)[0].build_ensemble(device=-2).program_signature()
     assert "LANES = 1" in sig2 and "STAGE_EXO = true" in sig2 and int(re.search(r"MIN_BLOCKS = (\d+)", sig2).group(1)) == 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_member_initial", [False, True])
+def test_eleven_box_chain_halocarbon_species_shared_among_lanes(per_member_initial, tmp_path, monkeypatch):
+    """In a lane-group program whose halocarbon emissions are exogenous, the 41 species are shared among the 32 lanes of a warp
+    (all members of a scenario compute the same concentrations) — unless an initial concentration is bound per member, which
+    the kernel finds out at the first step and then runs member by member.  Both against the oracle, with a NaN emission in
+    one scenario (latest_value fall-back) and a member count that leaves padding lanes."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    b, binds, p, scen = syn.full_chain(M=41, end=1920)
+    binds = dict(binds)
+    if per_member_initial:
+        binds["cfc11"] = "initial:Atmospheric Concentration|CFC-11"
+        p = np.concatenate([p, syn.uniform_params({"cfc11": (0.0, 300.0)}, 41, 5)], axis=1)
+    scen2 = {k: np.array(v, dtype=float) for k, v in scen[0].items()}
+    scen2["Emissions|CFC-12"][30] = np.nan
+    scen2["Emissions|SF6"] *= 3.0
+    ens = b.build_ensemble().bind_parameters(binds)
+    sc = ens.pack_scenarios([scen[0], scen2])
+    names = ["EESC", "Forcing|Halocarbons", "Forcing|F-gases", "Forcing|Montreal Gases", "Atmospheric Concentration|CFC-11",
+             "Atmospheric Concentration|CFC-12", "Atmospheric Concentration|SF6", "Atmospheric Concentration|CH3Cl", "Effective Radiative Forcing",
+             "Surface Temperature"]
+    ens.select_outputs(names)
+    got = ens.split_outputs(ens.run(p, sc))
+    m = oracle_from_builder(b)
+    ref = m.split(m.run_batch(oracle_bindings(b, binds), p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
+    if per_member_initial:
+        assert np.ptp(got["Atmospheric Concentration|CFC-11"][0]) > 100.0      # the bound initial values differ by member
