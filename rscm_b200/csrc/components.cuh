@@ -101,6 +101,16 @@ template <class R> struct StepCtx {
     double *xch;          // this member's exchange column: slot j at xch[j * 32]
 };
 
+// Output view for kinds with dozens of outputs (KindInfo::scatter_out): out[i] is the cell of the next time level the
+// i-th output value belongs to, so the solve writes its results where they live.  The first LIN_N outputs sit at cells
+// LIN_A + LIN_B i (a schema lists a component's series in order), which keeps the cell of a run-time index arithmetic; the
+// others are addressed with compile-time indices, so their table look-up folds away.
+template <class R, int LIN_N, int LIN_A, int LIN_B> struct ScatterOut {
+    R *cells;
+    const short *cell_of;
+    __device__ __forceinline__ R &operator[](int i) const { return i < LIN_N ? cells[LIN_A + LIN_B * i] : cells[cell_of[i]]; }
+};
+
 // Per-node literals the emitter passes: RK4 table row, offsets into ctab / sm / scratch / gtab, one kind-specific
 // integer (e.g. OceanCarbon's steps_per_year) that must be a compile-time constant, and the first exchange slot the
 // kind may use (lane groups; the slots before it carry the node's broadcast inputs).
@@ -236,6 +246,9 @@ __device__ __noinline__ double rscm_pow(double x, double y)
 }
 template <> __device__ __forceinline__ double r_pow<double>(double x, double y) { return rscm_pow(x, y); }
 template <> __device__ __forceinline__ float r_pow<float>(float x, float y) { return powf(x, y); }
+// an optimisation barrier for one value: what follows sees it as computed here
+__device__ __forceinline__ void r_keep(double &x) { asm volatile("" : "+d"(x)); }
+__device__ __forceinline__ void r_keep(float &x) { asm volatile("" : "+f"(x)); }
 template <class R> __device__ __forceinline__ R r_nan();
 template <> __device__ __forceinline__ double r_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
 template <> __device__ __forceinline__ float r_nan<float>() { return __int_as_float(0x7fc00000); }

@@ -231,6 +231,7 @@ static KindInfo halocarbon_kind()
     for (int i = 0; i < 2 * kHaloNS; ++i) k.in_access.push_back({i, 3});
     k.const_table = &halocarbon_const_table;
     k.no_slots = true;
+    k.scatter_out = true;
     return k;
 }
 
@@ -722,6 +723,28 @@ static void emit_program(Graph &g)
                 for (size_t i = 0; i < in_exprs.size(); ++i) o << (i ? ", " : "") << in_exprs[i];
                 if (in_exprs.empty()) o << "R(0)";
                 o << "};\n";
+            }
+            bool scatter = k->scatter_out;
+            for (size_t i = 0; i < n.out_var.size(); ++i) scatter = scatter && n.out_grid[i] == g.vars[n.out_var[i]].grid;
+            if (scatter) {
+                std::vector<int> oc;
+                for (size_t i = 0; i < n.out_var.size(); ++i)
+                    for (int r = 0; r < grid_regions(n.out_grid[i]); ++r) oc.push_back(g.vars[n.out_var[i]].cell0 + r);
+                // the longest arithmetic run of cells from the first output on
+                int lin_n = 1;
+                const int lin_b = oc.size() > 1 ? oc[1] - oc[0] : 0;
+                while (lin_n < static_cast<int>(oc.size()) && oc[lin_n] == oc[0] + lin_b * lin_n) ++lin_n;
+                o << "        constexpr short out_cell[" << n_out_vals << "] = {";
+                for (size_t i = 0; i < oc.size(); ++i) o << (i ? ", " : "") << oc[i];
+                o << "};\n        const rscm_dev::ScatterOut<R, " << lin_n << ", " << oc[0] << ", " << lin_b << "> out{nxt, out_cell};\n";
+                o << "        if (!" << solve_call << ") {\n            fail |= 1u;\n";
+                for (size_t i = 0; i < n.out_var.size(); ++i) {
+                    const Variable &var = g.vars[n.out_var[i]];
+                    for (int r = 0; r < var.n_regions; ++r) o << "            nxt[" << (var.cell0 + r) << "] = rscm_dev::r_nan<R>();\n";
+                }
+                o << "        }\n      }\n";
+                if (node_clocks) o << "      if (clk_on) node_clk[" << ni << "] += clock64() - clk_t;\n";
+                continue;
             }
             o << "        R out[" << n_out_vals << "];\n";
             o << "        if (" << solve_call << ") {\n";

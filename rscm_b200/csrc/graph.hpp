@@ -59,6 +59,9 @@ struct KindInfo {
     // may use n_xch further exchange slots (doubles per member) of its own.
     bool lane_aware = false;
     int n_xch = 0;
+    // the kind's solve is a template on its output argument: the emitter hands it a view that writes each output value into
+    // its cell of the next time level, instead of a local array it copies out afterwards (kinds with dozens of outputs)
+    bool scatter_out = false;
 };
 
 const KindInfo *kind_info(int kind);

@@ -387,8 +387,8 @@ __device__ __forceinline__ void halocarbon_species(const double *tab, int s, boo
     forcing = (new_conc - conc_pi) * rad_eff / R(1000);
 }
 
-template <class R>
-__device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R *in, R *out, const StepCtx<R> &cx, R *S, NodeRef nr)
+template <class R, class Out>
+__device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R *in, Out out, const StepCtx<R> &cx, R *S, NodeRef nr)
 {
     const double *tab = cx.ctab + nr.ctab;
     const R dt = R(cx.bounds[cx.N + 1] - cx.bounds[cx.N]);
@@ -428,6 +428,10 @@ __device__ inline bool halocarbon_chemistry_solve(const R *, const R *, const R 
                 const R ea = in[2 * sa], ca = in[2 * sa + 1], eb = in[2 * sb], cb = in[2 * sb + 1];
                 halocarbon_species<R>(tab, sa, uniform_dt, dt, ea, ca, S[0], nca, fa);
                 halocarbon_species<R>(tab, sb, uniform_dt, dt, eb, cb, S[1], ncb, fb);
+                // (the forcings are finished here, once per species: without this the compiler shuffles the numerators
+                // and divides by 1000 on every lane of every turn of the loop below)
+                r_keep(fa);
+                r_keep(fb);
             }
             HALO_CLK(0); // this lane's two species
 #pragma unroll 1
