@@ -415,7 +415,7 @@ static const std::vector<KindInfo> &kinds()
          48, /*n_state*/ 2, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10,
          /*scratch_fixed: 4 x 16 rows of block-prefix sums before the history (OCEAN_HIST0)*/ 64, /*no_slots*/ false, /*lanes*/ 1, /*aux_template*/ false,
          /*n_smem_lanes: as one CTA-wide region, two staged history tiles (8 words x 128 threads = 2 x 16 months x 32
-           members, OCEAN_KT in magicc_boxes.cuh)*/ 8, /*lane_aware*/ true, /*n_xch: the tiles' two mbarriers*/ 1},
+           members, OCEAN_KT in magicc_boxes.cuh) and their IRF windows (2 words = 2 x 128 lags)*/ 10, /*lane_aware*/ true, /*n_xch: the tiles' two mbarriers*/ 1},
     };
     static const bool extended = (k.push_back(halocarbon_kind()), true);
     (void)extended;
@@ -539,7 +539,7 @@ static void emit_program(Graph &g)
     int lanes_blocks = 3;
     const int tpad = (g.T + 3) / 4 * 4;
     const long lanes_smem = 16 + 1024 /*static + reserved per CTA*/ + (g.needs_time ? (tpad + 4) * 8L : 0) + static_cast<long>(g.ctab.size()) * 8 +
-                            static_cast<long>(g.n_rk) * tpad * 4 + g.n_smem * 1024L + g.n_xch * 256L + 2L * tpad * 8 /*one observed variable*/;
+                            static_cast<long>(g.n_rk) * tpad * 4 + g.n_smem * 1024L + g.n_xch * 256L;
     const long exo_smem = static_cast<long>(g.n_exo_rows) * tpad * 8;
     if (g.lanes > 1 && lanes_smem <= 232448 / 4) lanes_blocks = 4;
     if (const char *e = std::getenv("RSCM_B200_LANES_MIN_BLOCKS")) lanes_blocks = std::max(1, std::min(8, std::atoi(e))); // tuning knob
@@ -1090,6 +1090,7 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
                 for (int sp = 0; sp < kHaloNS; ++sp) g.ctab.push_back(std::exp(-dt_ref / tab[6 * sp]));
             }
         }
+        if (g.gtab.size() % 2) g.gtab.push_back(0.0); // every node's table starts on a 16-byte boundary (bulk copies of table windows)
         n.gtab_base = static_cast<int>(g.gtab.size());
         if (k->global_table) {
             std::string terr;

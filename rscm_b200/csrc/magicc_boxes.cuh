@@ -197,10 +197,12 @@ __device__ __forceinline__ bool n2o_chemistry_solve(const R *P, const R *, const
 //     per month is unchanged (history before the block, then the block, oldest first).
 // P: see include/rscm_b200.h (60 values); S[0] = months of history so far, S[1] = tiles staged so far (mbarrier phase).
 // Shared memory of the node in lane-group programs: as one CTA-wide region, OCEAN_KT / 2 words x 128 threads are the two
-// tiles [2][OCEAN_KT][32] (graph.cpp: n_smem_lanes); the tiles' two mbarriers are the node's exchange slot.  The prefix sums
+// tiles [2][OCEAN_KT][32], two more words the tiles' IRF windows [2][OCEAN_WIN] (graph.cpp: n_smem_lanes); the tiles' two
+// mbarriers are the node's exchange slot.  The prefix sums
 // wait for their year in the first 4 x 16 rows of the node's global scratch (row 16 q + m: month m of the block's year q;
 // 12 values per member and year through L2), the flux history follows from row OCEAN_HIST0 on.
 constexpr int OCEAN_KT = 16;
+constexpr int OCEAN_WIN = 128; // staged IRF window per tile: (16 + 4 x 16 - 1) entries at most, + 1 for the even start
 constexpr int OCEAN_HIST0 = 64;
 template <class R> __device__ __forceinline__ void ocean_carbon_prepare(const R *P, R *D)
 {
@@ -237,18 +239,19 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
     // same row length) against the lags of months `first_month + m` (m < steps), oldest entry first.  Chunks of 16 months:
     // sixteen independent loads in flight, and the IRF lags of a chunk form one sliding window of 15 + steps values
     // (uniform loads) instead of steps loads per month.
-    auto convolve = [&](const double *src, int i0, int i1, int first_month) {
+    // wt[lag]: the IRF table in global memory, or the staged window of a tile (shifted so that the lag indexes it).
+    auto convolve = [&](const double *src, int i0, int i1, int first_month, const double *wt) {
         constexpr int CH = 16;
         int i = i0;
         for (; i + CH <= i1; i += CH) {
             R f[CH];
 #pragma unroll
             for (int u = 0; u < CH; ++u) f[u] = R(src[(i + u) * SCR_LD]);
-            const double *wb = irf + (first_month - i - (CH - 1)); // wb[k]: lag first_month - i - (CH - 1) + k
+            const int l0 = first_month - i - (CH - 1); // wv[k]: lag l0 + k
             R wv[CH - 1 + MAXS];
 #pragma unroll
             for (int k = 0; k < CH - 1 + MAXS; ++k)
-                if (k < CH - 1 + steps) wv[k] = R(__ldg(wb + k));
+                if (k < CH - 1 + steps) wv[k] = R(wt[l0 + k]);
 #pragma unroll
             for (int u = 0; u < CH; ++u)
 #pragma unroll
@@ -257,15 +260,23 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
         }
         for (; i < i1; ++i) {
             const R f = R(src[i * SCR_LD]);
-            const double *w = irf + (first_month - i);
 #pragma unroll
             for (int m = 0; m < MAXS; ++m)
-                if (m < steps) acc[m] += f * R(__ldg(w + m));
+                if (m < steps) acc[m] += f * R(wt[first_month - i + m]);
         }
     };
     // a flux older than max_history_months has left the reference's deque: no need to load it (its weights are zero)
     const int max_hist = static_cast<int>(P[11]);
     auto oldest = [&](int first_month) { const int lo = first_month + 1 - max_hist; return lo > 0 ? (lo < n_old ? lo : n_old) : 0; };
+#ifdef RSCM_NODE_CLOCKS
+    __shared__ long long ocean_clk[5];
+    const bool clk_on = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    if (clk_on && cx.N == 0) for (int i = 0; i < 5; ++i) ocean_clk[i] = 0;
+    long long clk_t = clock64();
+#define OCEAN_CLK(i) do { if (clk_on) { const long long now_ = clock64(); ocean_clk[i] += now_ - clk_t; clk_t = now_; } } while (0)
+#else
+#define OCEAN_CLK(i) do { } while (0)
+#endif
     if (cx.lanes == 4) {
         const int yb = (n_old / steps) & 3;                               // year within the block of four (CTA-uniform)
         if (yb == 0) {
@@ -278,12 +289,19 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
             const int lo_cta = oldest(n_old), lo_role = oldest(first_month); // role 0 reaches furthest back
             const int nt = (n_old - lo_cta + OCEAN_KT - 1) / OCEAN_KT;
             const int tc = static_cast<int>(S[1]);
+            // the IRF lags the four roles need for the months [ts, te) of a tile: one window of (te - ts) + 4 steps - 1 table
+            // entries from lag n_old - te + 1 on, staged next to the tile (start rounded down to an even entry: 16-byte copies)
+            double *wins = tiles + 2 * OCEAN_KT * SCR_LD; // [2][OCEAN_WIN]
+            auto win0 = [&](int te) { return (n_old - te + 1) & ~1; };
             auto stage = [&](int t) { // thread 0 (lane 0 of the CTA's block: its `hist` is the block's row base)
-                const int ts = lo_cta + t * OCEAN_KT;
-                const unsigned bytes = static_cast<unsigned>((n_old - ts < OCEAN_KT ? n_old - ts : OCEAN_KT) * SCR_LD * 8);
+                const int ts = lo_cta + t * OCEAN_KT, te = ts + OCEAN_KT < n_old ? ts + OCEAN_KT : n_old;
+                const unsigned bytes = static_cast<unsigned>((te - ts) * SCR_LD * 8);
+                const int w0 = win0(te);
+                const unsigned wbytes = static_cast<unsigned>(((n_old + 4 * steps - ts - w0 + 1) & ~1) * 8);
                 void *bar = bars + ((tc + t) & 1);
-                mbar_expect_tx(bar, bytes);
+                mbar_expect_tx(bar, bytes + wbytes);
                 tma_bulk_g2s_stream(tiles + ((tc + t) & 1) * OCEAN_KT * SCR_LD, hist + static_cast<long long>(ts) * SCR_LD, bytes, bar);
+                tma_bulk_g2s(wins + ((tc + t) & 1) * OCEAN_WIN, irf + w0, wbytes, bar);
             };
             if (threadIdx.x == 0) {
                 if (nt > 0) stage(0);
@@ -292,9 +310,13 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
             for (int t = 0; t < nt; ++t) {
                 const int k = tc + t, ts = lo_cta + t * OCEAN_KT, te = ts + OCEAN_KT < n_old ? ts + OCEAN_KT : n_old;
                 mbar_wait(bars + (k & 1), (k >> 1) & 1);
-                convolve(tiles + (k & 1) * OCEAN_KT * SCR_LD + cx.col - ts * SCR_LD, ts > lo_role ? ts : lo_role, te, first_month);
+                OCEAN_CLK(0); // waiting for a tile
+                const double *win = wins + (k & 1) * OCEAN_WIN - win0(te); // win[lag]
+                convolve(tiles + (k & 1) * OCEAN_KT * SCR_LD + cx.col - ts * SCR_LD, ts > lo_role ? ts : lo_role, te, first_month, win);
+                OCEAN_CLK(1); // the tile's multiply-adds
                 __syncthreads(); // every warp is done with this tile: its buffer can take the tile after next
                 if (threadIdx.x == 0 && t + 2 < nt) stage(t + 2);
+                OCEAN_CLK(2); // rendezvous of the four roles
             }
             S[1] = R(tc + nt);
             if (cx.live) {
@@ -304,17 +326,19 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
             }
         }
         __syncthreads(); // (also makes the prefix sums, written by the member's other roles, visible to role 0)
+        OCEAN_CLK(3); // prefix sums out, rendezvous
         if (cx.role != 0) { // the other roles only help with the long history; role 0 steps the months
             S[0] = R(n_old + steps);
             return true;
         }
 #pragma unroll
         for (int m = 0; m < MAXS; ++m) acc[m] = (m < steps) ? R(pre[(16 * yb + m) * SCR_LD]) : R(0); // the sums role yb prepared
-        convolve(hist, n_old - yb * steps, n_old, n_old); // the block's own months so far (just written: L1 / L2 resident)
+        convolve(hist, n_old - yb * steps, n_old, n_old, irf); // the block's own months so far (just written: L1 / L2 resident)
+        OCEAN_CLK(3); // (+ prefix sums in, the block's own months)
     } else {
 #pragma unroll
         for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
-        convolve(hist, oldest(n_old), n_old, n_old);
+        convolve(hist, oldest(n_old), n_old, n_old, irf);
     }
     R fy[MAXS];
     R total_flux = R(0);
@@ -341,6 +365,12 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
             pco2 = (P[2] + dp) * tfac;
         }
     }
+    OCEAN_CLK(4); // role 0: the year's own months
+#ifdef RSCM_NODE_CLOCKS
+    if (clk_on && cx.N == cx.n_steps - 1)
+        printf("ocean_clocks tile_wait %lld multiply_adds %lld tile_rendezvous %lld prefix_out %lld months_of_the_year %lld (cycles per year)\n",
+               ocean_clk[0] / cx.n_steps, ocean_clk[1] / cx.n_steps, ocean_clk[2] / cx.n_steps, ocean_clk[3] / cx.n_steps, ocean_clk[4] / cx.n_steps);
+#endif
     if (cx.lanes == 4) fence_proxy_async(); // the months just written are staged by bulk copies from the next block of years on
     S[0] = R(n_old + steps);
     out[0] = total_flux;
