@@ -414,8 +414,8 @@ static const std::vector<KindInfo> &kinds()
           1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0},
          48, /*n_state*/ 2, /*n_smem*/ 0, /*scratch_per_T*/ 16, /*needs_time*/ true, {}, nullptr, &ocean_irf_table, /*aux_param*/ 10,
          /*scratch_fixed: 4 x 16 rows of block-prefix sums before the history (OCEAN_HIST0)*/ 64, /*no_slots*/ false, /*lanes*/ 1, /*aux_template*/ false,
-         /*n_smem_lanes: as one CTA-wide region, two staged history tiles (8 words x 128 threads = 2 x 16 months x 32
-           members, OCEAN_KT in magicc_boxes.cuh) and their IRF windows (2 words = 2 x 128 lags)*/ 10, /*lane_aware*/ true, /*n_xch: the tiles' two mbarriers*/ 1},
+         /*n_smem_lanes: as one CTA-wide region, two staged history tiles (16 words x 128 threads = 2 x 32 months x 32
+           members, OCEAN_KT in magicc_boxes.cuh) and their IRF windows (2 words = 2 x 128 lags)*/ 18, /*lane_aware*/ true, /*n_xch: the tiles' two mbarriers*/ 1},
     };
     static const bool extended = (k.push_back(halocarbon_kind()), true);
     (void)extended;
@@ -1055,11 +1055,11 @@ bool compile_graph(const rscm_b200_graph_desc &d, Graph &g, std::string &err)
         if (k->aux_param >= 0) n.aux = static_cast<int>(n.params[k->aux_param]);
         // stateful kinds: per-thread state, shared-memory scratch, global scratch, per-graph constant tables
         n.state_base = g.n_state;
-        n.smem_base = g.n_smem;
+        n.smem_base = 0; // per-thread shared-memory words hold nothing between two solves: every node uses the same ones
         n.scratch_base = g.n_scratch_rows;
         n.ctab_base = static_cast<int>(g.ctab.size());
         g.n_state += k->n_state;
-        g.n_smem += k->n_smem + (g.lanes > 1 ? k->n_smem_lanes : 0);
+        g.n_smem = std::max(g.n_smem, k->n_smem + (g.lanes > 1 ? k->n_smem_lanes : 0));
         if (g.lanes > 1 && (k->lanes > 1 || k->lane_aware)) {
             // a lane node: its input values travel from role 0 to the other roles through the first exchange slots
             n.lane_node = true;

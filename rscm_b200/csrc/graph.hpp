@@ -37,7 +37,8 @@ struct KindInfo {
     int reg_weight;            // rough register appetite; decides the kernel's min-CTAs-per-SM hint
     // stateful kinds (ClimateUDEB, ...): sizes of the per-thread state the fused kernel provides
     int n_state = 0;       // register/local values (R S[])
-    int n_smem = 0;        // per-thread shared-memory scratch, in 8-byte words (both compute dtypes)
+    int n_smem = 0;        // per-thread shared-memory scratch, in 8-byte words (both compute dtypes); it holds nothing
+                           // between two solves, so the nodes of a program share the same words (the program takes the largest)
     int scratch_per_T = 0; // global scratch rows per time point (member-interleaved)
     bool needs_time = false; // solve uses the time bounds
     // input access override: (input index, mode) per `in[]` entry group; mode 0 = get(), 1 = at_start, 2 = at_end.

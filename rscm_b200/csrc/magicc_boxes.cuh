@@ -201,8 +201,8 @@ __device__ __forceinline__ bool n2o_chemistry_solve(const R *P, const R *, const
 // mbarriers are the node's exchange slot.  The prefix sums
 // wait for their year in the first 4 x 16 rows of the node's global scratch (row 16 q + m: month m of the block's year q;
 // 12 values per member and year through L2), the flux history follows from row OCEAN_HIST0 on.
-constexpr int OCEAN_KT = 16;
-constexpr int OCEAN_WIN = 128; // staged IRF window per tile: (16 + 4 x 16 - 1) entries at most, + 1 for the even start
+constexpr int OCEAN_KT = 32;
+constexpr int OCEAN_WIN = 128; // staged IRF window per tile: (32 + 4 x 16 - 1) entries at most, + 1 for the even start
 constexpr int OCEAN_HIST0 = 64;
 template <class R> __device__ __forceinline__ void ocean_carbon_prepare(const R *P, R *D)
 {
