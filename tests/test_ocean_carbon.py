@@ -253,3 +253,20 @@ def test_eleven_box_chain_halocarbon_species_shared_among_lanes(per_member_initi
         assert rel_err(got[n], ref[n]) <= 1e-9, n
     if per_member_initial:
         assert np.ptp(got["Atmospheric Concentration|CFC-11"][0]) > 100.0      # the bound initial values differ by member
+
+
+@pytest.mark.gpu
+def test_eleven_box_chain_fp32_path_within_1e4(tmp_path, monkeypatch):
+    """The optional fp32 path (bar: 1e-4) on the widest graph over a century: the history tiles, prefix sums and exchange slots
+    stay fp64, the arithmetic is fp32."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    b, binds, p, scen = syn.full_chain(M=70, end=1950)
+    names = syn.FULL_CHAIN_OUTPUTS + ["Ocean Surface pCO2", "Ocean Heat Content"]
+    ens = b.build_ensemble(dtype="f32").bind_parameters(binds)
+    ens.select_outputs(names)
+    sc = ens.pack_scenarios(scen)
+    got = ens.split_outputs(ens.run(p, sc))
+    m = oracle_from_builder(b)
+    ref = m.split(m.run_batch(oracle_bindings(b, binds), p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-4, n
