@@ -74,17 +74,17 @@ __device__ __forceinline__ double r_rcp(double x)
 }
 __device__ __forceinline__ float r_rcp(float x) { return __frcp_rn(x); }
 
-template <class R> __device__ __forceinline__ void udeb_fractions(const R *P, R (&a)[4])
+template <class R, class PT = R> __device__ __forceinline__ void udeb_fractions(const PT *P, R (&a)[4])
 {
-    const R fgnl = P[U_NH_LAND] / R(2), fgsl = P[U_SH_LAND] / R(2);
+    const R fgnl = R(P[U_NH_LAND]) / R(2), fgsl = R(P[U_SH_LAND]) / R(2);
     a[0] = R(0.5) - fgnl; a[1] = fgnl; a[2] = R(0.5) - fgsl; a[3] = fgsl;
 }
 
-template <class R> __device__ __forceinline__ void udeb_qfrac(const R *P, const R (&area)[4], R (&q)[4])
+template <class R, class PT = R> __device__ __forceinline__ void udeb_qfrac(const PT *P, const R (&area)[4], R (&q)[4])
 {
     R s = R(0);
-    for (int i = 0; i < 4; ++i) s += P[U_RFR0 + i] * area[i];
-    for (int i = 0; i < 4; ++i) q[i] = (r_abs(s) <= R(1e-15)) ? R(1) : P[U_RFR0 + i] / s;
+    for (int i = 0; i < 4; ++i) s += R(P[U_RFR0 + i]) * area[i];
+    for (int i = 0; i < 4; ++i) q[i] = (r_abs(s) <= R(1e-15)) ? R(1) : R(P[U_RFR0 + i]) / s;
 }
 
 // lamcalc — hybrid step / secant iteration on lambda_ocean, tolerance 1e-3 on the land/ocean warming ratio.
@@ -94,13 +94,16 @@ template <class R> __device__ __forceinline__ void udeb_qfrac(const R *P, const 
 //   [ -k_ns    0       A2     -k_lo ]      solved here by Cramer's rule (same solution up to rounding; the
 //   [ 0        0      -k_lo*a  B3   ]      singular-pivot failure becomes a vanishing B1, B3 or determinant).
 // Only the last three iterates of the reference's lamo[]/diff[] arrays are ever read: kept as scalars.
-template <class R> __device__ inline bool udeb_lamcalc(const R *P, R ecs, R &lam_o_out, R &lam_l_out, R &eff_out)
+// (R = the arithmetic, PT = the type the parameters are stored in: the fp32 path runs LAMCALC in fp64 — its secant
+// iteration stops at the first iterate with |diff| < 0.001, and which iterate that is must not depend on the precision:
+// stopping one iterate earlier or later moves the feedback parameters by up to 1e-3)
+template <class R, class PT = R> __device__ inline bool udeb_lamcalc(const PT *P, R ecs, R &lam_o_out, R &lam_l_out, R &eff_out)
 {
     constexpr int MAXIT = 40;
-    const R q2x = P[U_RF2X], k_lo = P[U_KLO], k_ns = P[U_KNS], rlo = P[U_RLO], alpha = P[U_AMP];
+    const R q2x = R(P[U_RF2X]), k_lo = R(P[U_KLO]), k_ns = R(P[U_KNS]), rlo = R(P[U_RLO]), alpha = R(P[U_AMP]);
     R area[4], qfrac[4];
-    udeb_fractions(P, area);
-    udeb_qfrac(P, area, qfrac);
+    udeb_fractions<R, PT>(P, area);
+    udeb_qfrac<R, PT>(P, area, qfrac);
     const R fgno = area[0], fgnl = area[1], fgso = area[2], fgsl = area[3];
     const R lam = q2x / ecs;
     const R fratio = (fgno + fgso) / (fgnl + fgsl);
@@ -129,7 +132,7 @@ template <class R> __device__ inline bool udeb_lamcalc(const R *P, R ecs, R &lam
         const R d2 = rlo - land_mean / ocean_mean;
         if (r_abs(d2) < R(0.001)) {
             R rf_sum = R(0);
-            for (int c = 0; c < 4; ++c) rf_sum += P[U_RFR0 + c] * area[c];
+            for (int c = 0; c < 4; ++c) rf_sum += R(P[U_RFR0 + c]) * area[c];
             R eff = R(1);
             if (r_abs(rf_sum) > R(1e-15)) eff = (area[0] * t0 + area[1] * t1 + area[2] * t2 + area[3] * t3) / ecs;
             lam_o_out = lam_o; lam_l_out = lam_l; eff_out = eff;
@@ -213,7 +216,9 @@ template <class R, int N> __device__ inline void climate_udeb_init_state(const R
     udeb_fractions(P, area);
     udeb_qfrac(P, area, q);
     R lo = R(0), ll = R(0), ef = R(1);
-    const bool ok = (P[U_EFF_CO2] > R(0)) && (P[U_EFF_CO2] == P[U_EFF_CO2]) && udeb_lamcalc(P, P[U_ECS], lo, ll, ef);
+    double lo_d = 0.0, ll_d = 0.0, ef_d = 1.0;
+    const bool ok = (P[U_EFF_CO2] > R(0)) && (P[U_EFF_CO2] == P[U_EFF_CO2]) && udeb_lamcalc<double, R>(P, static_cast<double>(P[U_ECS]), lo_d, ll_d, ef_d);
+    lo = R(lo_d); ll = R(ll_d); ef = R(ef_d);
     S[US_OK] = ok ? R(1) : R(0);
     S[US_LAMO] = lo; S[US_LAML] = ll; S[US_EFF] = ef;
     for (int i = 0; i < 4; ++i) S[US_QF0 + i] = q[i];
@@ -465,8 +470,8 @@ __device__ inline bool climate_udeb_solve(const R *P, const R *, const R *in, R 
         const R aecs = P[U_ECS] * cumt_factor * q_factor;
         R lo = S[US_LAMO], ll = S[US_LAML], ef = S[US_EFF];
         if (r_abs(aecs - P[U_ECS]) > R(1e-10)) {
-            R lo2, ll2, ef2;
-            if (udeb_lamcalc(P, aecs, lo2, ll2, ef2)) { lo = lo2; ll = ll2; ef = ef2; }
+            double lo2, ll2, ef2;
+            if (udeb_lamcalc<double, R>(P, static_cast<double>(aecs), lo2, ll2, ef2)) { lo = R(lo2); ll = R(ll2); ef = R(ef2); }
         }
         X[UX_LAM * 32] = static_cast<double>(lo);
         X[(UX_LAM + 1) * 32] = static_cast<double>(ll);
