@@ -270,3 +270,26 @@ def test_eleven_box_chain_fp32_path_within_1e4(tmp_path, monkeypatch):
     ref = m.split(m.run_batch(oracle_bindings(b, binds), p, ens.exogenous_names, sc, names), names)
     for n in names:
         assert rel_err(got[n], ref[n]) <= 1e-4, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("steps", [7, 16])
+def test_eleven_box_chain_with_other_ocean_step_counts(steps, tmp_path, monkeypatch):
+    """OceanCarbon's staged tiles and IRF windows with an odd number of months per year (the bulk copies of the table window
+    start on even entries: the offset inside the window changes from block to block) and with the largest one."""
+    monkeypatch.setenv("RSCM_B200_CACHE", str(tmp_path))
+    from rscm_b200.magicc import OceanCarbonBuilder as OCB
+    b = full_magicc_builder(end=1930)
+    for i, c in enumerate(b._components):
+        if c.type_name == "OceanCarbon":
+            b._components[i] = OCB.from_parameters({"steps_per_year": steps}).build()
+    ens = b.build_ensemble().bind_parameters(FULL_BINDS)
+    sc = ens.pack_scenarios([full_magicc_scenario(end=1930)])
+    p = syn.uniform_params({"ecs": (2.0, 4.5), "beta": (0.4, 0.9), "tau": (6.5, 9.5), "tau_oh": (8.5, 10.5)}, 33, 47)
+    names = ["Atmospheric Concentration|CO2", "Carbon Flux|Ocean", "Ocean Surface pCO2", "Cumulative Ocean Uptake", "Surface Temperature"]
+    ens.select_outputs(names)
+    got = ens.split_outputs(ens.run(p, sc))
+    m = oracle_from_builder(b)
+    ref = m.split(m.run_batch(oracle_bindings(b, FULL_BINDS), p, ens.exogenous_names, sc, names), names)
+    for n in names:
+        assert rel_err(got[n], ref[n]) <= 1e-9, n
