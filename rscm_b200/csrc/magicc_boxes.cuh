@@ -325,16 +325,37 @@ __device__ inline bool ocean_carbon_solve(const R *P, const R *D, const R *in, R
                     if (m < steps) pre[(16 * cx.role + m) * SCR_LD] = static_cast<double>(acc[m]);
             }
         }
-        __syncthreads(); // (also makes the prefix sums, written by the member's other roles, visible to role 0)
+        __syncthreads(); // (also makes the prefix sums, written by the member's other roles, visible)
         OCEAN_CLK(3); // prefix sums out, rendezvous
-        if (cx.role != 0) { // the other roles only help with the long history; role 0 steps the months
-            S[0] = R(n_old + steps);
-            return true;
-        }
+        // The block's own months so far (up to three years, just written by role 0: L2) are added by all four roles, four
+        // of the year's sums each (months 4 q .. 4 q + 3, in the same order: history before the block, then the block,
+        // oldest first), and handed to role 0.
+        {
+            const int m0 = 4 * cx.role;
+            R part[4];
 #pragma unroll
-        for (int m = 0; m < MAXS; ++m) acc[m] = (m < steps) ? R(pre[(16 * yb + m) * SCR_LD]) : R(0); // the sums role yb prepared
-        convolve(hist, n_old - yb * steps, n_old, n_old, irf); // the block's own months so far (just written: L1 / L2 resident)
-        OCEAN_CLK(3); // (+ prefix sums in, the block's own months)
+            for (int u = 0; u < 4; ++u) part[u] = (m0 + u < steps) ? R(pre[(16 * yb + m0 + u) * SCR_LD]) : R(0); // the sums role yb prepared
+#pragma unroll 4
+            for (int i = n_old - yb * steps; i < n_old; ++i) {
+                const R f = R(hist[i * SCR_LD]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (m0 + u < steps) part[u] += f * R(irf[n_old - i + m0 + u]);
+            }
+            // (handed over through the tile area, idle outside the staging above; like every per-thread shared-memory word it
+            // holds nothing beyond this solve: ClimateUDEB's column uses the same words)
+            double *xa = reinterpret_cast<double *>(cx.sm - threadIdx.x) + nr.sm * BLOCK + (threadIdx.x & 31); // sum m at xa[m * 32]
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xa[(m0 + u) * 32] = static_cast<double>(part[u]);
+            __syncthreads();
+            if (cx.role != 0) { // the other roles only help with the history; role 0 steps the months
+                S[0] = R(n_old + steps);
+                return true;
+            }
+#pragma unroll
+            for (int m = 0; m < MAXS; ++m) acc[m] = (m < steps) ? R(xa[m * 32]) : R(0);
+        }
+        OCEAN_CLK(3); // (+ the block's own months)
     } else {
 #pragma unroll
         for (int m = 0; m < MAXS; ++m) acc[m] = R(0);
